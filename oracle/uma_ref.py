@@ -1,0 +1,297 @@
+"""PyTorch restatement of the UMA-S (eSCN-MD backbone + MoLE + MLP energy head) evaluation.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``; PARITY UNPINNED).  Restates, from the published
+fairchem-core v2 algorithm, what the reference executes inside
+``self.predict.predict(batch)`` (``pdb2reaction/uma_pysis.py:385``) and
+``torch.autograd.functional.hessian`` (``uma_pysis.py:402-408``):
+
+  models/uma/escn_md.py        eSCNMDBackbone.forward, MLP_EFS_Head      -> ``energy``
+  models/uma/escn_moe.py       MoLE routing / merge                      -> ``mole_weight``
+  models/uma/escn_md_block.py  Edgewise, SpectralAtomwise, eSCNMD_Block  -> ``edgewise``, ``ffn``
+  models/uma/nn/so2_layers.py  SO2_Convolution, SO2_m_Conv               -> ``so2_conv``
+  models/uma/nn/so3_layers.py  SO3_Linear                                -> ``so3_linear``
+  models/uma/nn/radial.py      RadialMLP, GaussianSmearing, envelope     -> ``radial_mlp`` ...
+  models/uma/nn/layer_norm.py  EquivariantRMSNormArraySphericalHarmonicsV2 -> ``rms_norm_sh``
+  models/uma/nn/activation.py  GateActivation                            -> ``gate_act``
+
+Normaliser = identity and element references = 0 (random-init weights).
+Forces come from autograd, exactly as the reference's conservative head does.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import graph as ograph
+from . import wigner as owigner
+
+DATASET_LIST = ("oc20", "omol", "omat", "odac", "omc")
+TO_M = (0, 2, 6, 3, 7, 1, 5, 8, 4)          # m-primary row -> l-primary index (lmax = mmax = 2)
+L_OF = (0, 1, 1, 1, 2, 2, 2, 2, 2)          # l of each l-primary coefficient
+GATE_IDX_M = (0, 1, 0, 1, 0, 1, 1, 1)       # l-1 of m-primary rows 1..8
+GATE_IDX_L = (0, 0, 0, 1, 1, 1, 1, 1)       # l-1 of l-primary rows 1..8
+
+
+class Hyper:
+    def __init__(self, **kw):
+        self.C = kw.get("sphere_channels", 128)
+        self.H = kw.get("hidden_channels", 128)
+        self.Ce = kw.get("edge_channels", 128)
+        self.lmax = kw.get("lmax", 2)
+        self.num_layers = kw.get("num_layers", 4)
+        self.B = kw.get("num_distance_basis", 64)
+        self.cutoff = kw.get("cutoff", 6.0)
+        self.max_neighbors = kw.get("max_neighbors", 300)
+        self.num_experts = kw.get("num_experts", 32)
+        self.rescale = kw.get("edge_degree_rescale", 5.0)
+        self.eps = kw.get("norm_eps", 1e-5)
+        assert self.lmax == 2, "oracle restates lmax = mmax = 2 only"
+
+
+# ------------------------------------------------------------------ small pieces
+def gaussian_smearing(d, hp: Hyper):
+    offset = torch.linspace(0.0, hp.cutoff, hp.B, dtype=d.dtype)
+    coeff = -0.5 / (2.0 * (offset[1] - offset[0])) ** 2
+    return torch.exp(coeff * (d[:, None] - offset[None, :]) ** 2)
+
+
+def polynomial_envelope(d, hp: Hyper, p: int = 5):
+    u = d / hp.cutoff
+    a = -(p + 1) * (p + 2) / 2.0
+    b = p * (p + 2.0)
+    c = -p * (p + 1) / 2.0
+    env = 1.0 + a * u**p + b * u ** (p + 1) + c * u ** (p + 2)
+    return torch.where(u < 1.0, env, torch.zeros_like(env))
+
+
+def radial_mlp(w, name, x):
+    for i in (1, 2):
+        x = F.linear(x, w[f"{name}.lin{i}.weight"], w[f"{name}.lin{i}.bias"])
+        x = F.layer_norm(x, (x.shape[-1],), w[f"{name}.ln{i}.weight"], w[f"{name}.ln{i}.bias"], 1e-5)
+        x = F.silu(x)
+    return F.linear(x, w[f"{name}.lin3.weight"], w[f"{name}.lin3.bias"])
+
+
+def rms_norm_sh(x, w_aff, b_aff, hp: Hyper):
+    x0 = x[:, 0:1, :]
+    x0 = x0 - x0.mean(dim=2, keepdim=True)
+    feat = torch.cat([x0, x[:, 1:, :]], dim=1)
+    bw = torch.tensor([1.0 / ((2 * l + 1) * (hp.lmax + 1)) for l in L_OF], dtype=x.dtype)
+    fn = (feat.pow(2) * bw.view(1, -1, 1)).sum(dim=1, keepdim=True)
+    fn = fn.mean(dim=2, keepdim=True)
+    fn = (fn + hp.eps).pow(-0.5)
+    out = feat * fn * w_aff[list(L_OF)].unsqueeze(0)
+    return torch.cat([out[:, 0:1, :] + b_aff.view(1, 1, -1), out[:, 1:, :]], dim=1)
+
+
+def gate_act(gate, x, idx, n_ch):
+    g = torch.sigmoid(gate).reshape(gate.shape[0], 2, n_ch)[:, list(idx), :]
+    return torch.cat([F.silu(x[:, 0:1, :]), x[:, 1:, :] * g], dim=1)
+
+
+def mole_weight(w, key, coeff):
+    wt = w[key]
+    if wt.dim() == 3:                      # un-merged experts [X, out, in]
+        return torch.einsum("e,eoi->oi", coeff, wt)
+    return wt
+
+
+def so2_conv(w, prefix, x, rad, cin, cout, extra, coeff):
+    """x [E,9,cin] m-primary; rad [E, 6*cin] or None -> ([E,9,cout], gate [E,extra] or None)."""
+    e = x.shape[0]
+    x0 = x[:, 0:3, :].reshape(e, 3 * cin)
+    if rad is not None:
+        x0 = x0 * rad[:, : 3 * cin]
+    y0 = F.linear(x0, mole_weight(w, prefix + ".fc_m0.weight", coeff), w[prefix + ".fc_m0.bias"])
+    gate = y0[:, :extra] if extra else None
+    outs = [y0[:, extra:].reshape(e, 3, cout)]
+    off, roff = 3, 3 * cin
+    for m in (1, 2):
+        n_m = 3 - m
+        xm = x[:, off:off + 2 * n_m, :].reshape(e, 2, n_m * cin)
+        if rad is not None:
+            xm = xm * rad[:, roff:roff + n_m * cin].unsqueeze(1)
+        ym = F.linear(xm, mole_weight(w, f"{prefix}.fc_m{m}.weight", coeff))
+        half = n_m * cout
+        yr, yi = ym[..., :half], ym[..., half:]
+        o_r = yr[:, 0] - yi[:, 1]
+        o_i = yr[:, 1] + yi[:, 0]
+        outs.append(torch.stack([o_r, o_i], dim=1).reshape(e, 2 * n_m, cout))
+        off += 2 * n_m
+        roff += n_m * cin
+    return torch.cat(outs, dim=1), gate
+
+
+def so3_linear(x, weight, bias):
+    wexp = weight[list(L_OF)]                                 # [9, out, in]
+    out = torch.einsum("nmi,moi->nmo", x, wexp)
+    return torch.cat([out[:, 0:1, :] + bias.view(1, 1, -1), out[:, 1:, :]], dim=1)
+
+
+# ------------------------------------------------------------------ blocks
+def edgewise(w, p, x, x_edge, src, tgt, wig_m, wig_m_inv_env, hp, coeff, edge_chunk=None):
+    n = x.shape[0]
+    out = x.new_zeros(n, 9, hp.C)
+    e_tot = src.shape[0]
+    step = e_tot if not edge_chunk else int(edge_chunk)
+    for s in range(0, max(e_tot, 1), max(step, 1)):
+        sl = slice(s, min(e_tot, s + step))
+        msg = torch.cat([x[src[sl]], x[tgt[sl]]], dim=2)
+        msg = torch.bmm(wig_m[sl], msg)
+        rad = radial_mlp(w, p + ".edge.conv1.rad", x_edge[sl])
+        msg, gate = so2_conv(w, p + ".edge.conv1", msg, rad, 2 * hp.C, hp.H, 2 * hp.H, coeff)
+        msg = gate_act(gate, msg, GATE_IDX_M, hp.H)
+        msg, _ = so2_conv(w, p + ".edge.conv2", msg, None, hp.H, hp.C, 0, coeff)
+        msg = torch.bmm(wig_m_inv_env[sl], msg)
+        out = out.index_add(0, tgt[sl], msg)
+    return out
+
+
+def ffn(w, p, x, hp):
+    g = F.silu(F.linear(x[:, 0, :], w[p + ".ffn.scalar_mlp.weight"], w[p + ".ffn.scalar_mlp.bias"]))
+    x = so3_linear(x, w[p + ".ffn.so3_1.weight"], w[p + ".ffn.so3_1.bias"])
+    x = gate_act(g, x, GATE_IDX_L, hp.H)
+    return so3_linear(x, w[p + ".ffn.so3_2.weight"], w[p + ".ffn.so3_2.bias"])
+
+
+def system_embedding(w, charge, spin, task_name):
+    e = torch.cat([w["charge_embedding.weight"][int(charge) + 100],
+                   w["spin_embedding.weight"][int(spin)],
+                   w["dataset_embedding.weight"][DATASET_LIST.index(task_name)]])
+    return F.silu(F.linear(e, w["mix_csd.weight"], w["mix_csd.bias"]))
+
+
+def routing(w, z, csd):
+    comp = w["composition_embedding.weight"][z].mean(dim=0)
+    h = torch.cat([comp, csd])
+    h = F.silu(F.linear(h, w["routing_mlp.0.weight"], w["routing_mlp.0.bias"]))
+    h = F.silu(F.linear(h, w["routing_mlp.2.weight"], w["routing_mlp.2.bias"]))
+    return torch.softmax(F.linear(h, w["routing_mlp.4.weight"], w["routing_mlp.4.bias"]), dim=0)
+
+
+# ------------------------------------------------------------------ full model
+def energy(w: Dict[str, torch.Tensor], pos: torch.Tensor, z: torch.Tensor, natoms: Sequence[int],
+           edge_index: torch.Tensor, *, charge=0, spin=1, task_name="omol", hp: Optional[Hyper] = None,
+           gamma=None, edge_chunk=None, return_parts=False):
+    """Per-image energies [n_images] (eV).  All images share composition/charge/spin/task (one
+    calculator = one composition, reference ``uma_pysis.py:502-504``).
+
+    ``w`` may hold merged ([out,in]) or un-merged ([X,out,in]) SO(2) weights.
+    """
+    hp = hp or Hyper()
+    dt = pos.dtype
+    w = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in w.items()}
+    n_img = len(natoms)
+    n0 = int(natoms[0])
+    src, tgt = edge_index[0], edge_index[1]
+
+    csd = system_embedding(w, charge, spin, task_name)
+    coeff = routing(w, z[:n0], csd)
+
+    vec = pos[src] - pos[tgt]
+    dist = vec.norm(dim=1)
+    x_edge = torch.cat([gaussian_smearing(dist, hp),
+                        w["source_embedding.weight"][z[src]],
+                        w["target_embedding.weight"][z[tgt]]], dim=1)
+    env = polynomial_envelope(dist, hp)
+    wig = owigner.edge_wigner(vec, hp.lmax, gamma)             # [E,9,9] l-primary
+    wig_m = wig[:, list(TO_M), :]                               # to_m . D
+    wig_m_inv_env = wig.transpose(1, 2)[:, :, list(TO_M)] * env.view(-1, 1, 1)   # D^T . to_m^T * env
+
+    n = pos.shape[0]
+    x0 = w["sphere_embedding.weight"][z] + csd.view(1, -1)
+    x = torch.cat([x0.unsqueeze(1), pos.new_zeros(n, 8, hp.C)], dim=1)
+
+    # edge-degree embedding
+    rad = radial_mlp(w, "edge_degree.rad", x_edge).reshape(-1, 3, hp.C)
+    ed = torch.cat([rad, rad.new_zeros(rad.shape[0], 6, hp.C)], dim=1)
+    ed = torch.bmm(wig_m_inv_env, ed) / hp.rescale
+    x = x + x.new_zeros(n, 9, hp.C).index_add(0, tgt, ed)
+
+    for l in range(hp.num_layers):
+        p = f"blocks.{l}"
+        res = x
+        h = rms_norm_sh(x, w[p + ".norm_1.affine_weight"], w[p + ".norm_1.affine_bias"], hp)
+        h = torch.cat([h[:, 0:1, :] + csd.view(1, 1, -1), h[:, 1:, :]], dim=1)
+        h = edgewise(w, p, h, x_edge, src, tgt, wig_m, wig_m_inv_env, hp, coeff, edge_chunk)
+        x = res + h
+        res = x
+        h = rms_norm_sh(x, w[p + ".norm_2.affine_weight"], w[p + ".norm_2.affine_bias"], hp)
+        h = ffn(w, p, h, hp)
+        x = res + h
+    x = rms_norm_sh(x, w["norm.affine_weight"], w["norm.affine_bias"], hp)
+
+    s = x[:, 0, :]
+    s = F.silu(F.linear(s, w["head.0.weight"], w["head.0.bias"]))
+    s = F.silu(F.linear(s, w["head.2.weight"], w["head.2.bias"]))
+    node_e = F.linear(s, w["head.4.weight"], w["head.4.bias"]).view(-1)
+    img = torch.repeat_interleave(torch.arange(n_img), torch.as_tensor(list(natoms)))
+    e_img = node_e.new_zeros(n_img).index_add(0, img, node_e)
+    if return_parts:
+        return e_img, {"node_energy": node_e, "x_final": x, "x_edge": x_edge, "env": env,
+                       "wigner": wig, "csd": csd, "coeff": coeff, "dist": dist, "vec": vec}
+    return e_img
+
+
+class OracleUMA:
+    """Convenience wrapper: graph build (float32 positions, as ``AtomicData.from_ase`` does)
+    + energy + autograd forces / Hessian, batch of images of one composition."""
+
+    def __init__(self, weights: Dict[str, torch.Tensor], z: Sequence[int], *, charge=0, spin=1,
+                 task_name="omol", dtype=torch.float32, hyper: Optional[Hyper] = None,
+                 max_neighbors=None, cutoff=None, edge_chunk=None):
+        self.hp = hyper or Hyper()
+        if cutoff is not None:
+            self.hp.cutoff = float(cutoff)
+        if max_neighbors is not None:
+            self.hp.max_neighbors = int(max_neighbors)
+        self.w = weights
+        self.z1 = [int(v) for v in z]
+        self.charge, self.spin, self.task_name = charge, spin, task_name
+        self.dtype = dtype
+        self.edge_chunk = edge_chunk
+
+    def graph(self, pos_f32: np.ndarray, natoms):
+        return ograph.radius_graph(pos_f32, natoms, self.hp.cutoff, self.hp.max_neighbors)
+
+    def _prep(self, coords):
+        c = np.asarray(coords, dtype=np.float64)
+        if c.ndim == 2:
+            c = c[None]
+        n_img, n, _ = c.shape
+        assert n == len(self.z1)
+        pos32 = c.reshape(-1, 3).astype(np.float32)          # graph + model see float32 positions
+        natoms = [n] * n_img
+        ei = torch.from_numpy(self.graph(pos32, natoms))
+        z = torch.tensor(self.z1 * n_img, dtype=torch.long)
+        pos = torch.from_numpy(pos32).to(self.dtype)
+        return pos, z, natoms, ei
+
+    def energy_forces(self, coords, forces=True, gamma=None):
+        """coords [B,N,3] or [N,3] Angstrom -> (E [B] eV, F [B,N,3] eV/A or None)."""
+        pos, z, natoms, ei = self._prep(coords)
+        pos.requires_grad_(forces)
+        e = energy(self.w, pos, z, natoms, ei, charge=self.charge, spin=self.spin,
+                   task_name=self.task_name, hp=self.hp, gamma=gamma, edge_chunk=self.edge_chunk)
+        f = None
+        if forces:
+            (g,) = torch.autograd.grad(e.sum(), pos)
+            f = (-g).reshape(len(natoms), -1, 3).detach()
+        return e.detach(), f
+
+    def hessian(self, coords):
+        """Analytic Hessian of ONE image by double backward at a fixed edge set:
+        (N,3,N,3) eV/A^2 (reference ``uma_pysis.py:402-409``)."""
+        pos, z, natoms, ei = self._prep(coords)
+        assert len(natoms) == 1
+
+        def e_fn(flat):
+            return energy(self.w, flat.view(-1, 3), z, natoms, ei, charge=self.charge,
+                          spin=self.spin, task_name=self.task_name, hp=self.hp).squeeze()
+
+        h = torch.autograd.functional.hessian(e_fn, pos.reshape(-1), vectorize=False)
+        n = natoms[0]
+        return h.view(n, 3, n, 3).detach()

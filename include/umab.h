@@ -1,0 +1,106 @@
+/* umab -- C ABI of the B200-native UMA (eSCN-MD + MoLE) energy / force engine.
+ *
+ * This is the drop-in boundary for pdb2reaction's one data-parallel hot path.  The reference
+ * is pure Python and has no FFI of its own; the interface each entry point replaces is the
+ * fairchem call the reference's calculator makes (file:line into /root/reference):
+ *
+ *   umab_create / umab_set_weight / umab_finalize_weights
+ *        <- pretrained_mlip.get_predict_unit(model, device=...)        pdb2reaction/uma_pysis.py:246-250
+ *           (+ the MoLE merge fairchem does per system; done on the host once per calculator)
+ *   umab_set_system
+ *        <- UMAcore.__init__ latching elem / charge / spin / task      pdb2reaction/uma_pysis.py:266-269
+ *   umab_build_graph (+ umab_graph_counts / umab_graph_copy)
+ *        <- AtomicData.from_ase + data_list_collater(otf_graph=True)    pdb2reaction/uma_pysis.py:313-322
+ *   umab_energy_forces / umab_energy_forces_host
+ *        <- self.predict.predict(batch) (energy + conservative forces)  pdb2reaction/uma_pysis.py:385-392
+ *           called once per image by the reference; here once per BATCH of images
+ *           (GSM/DMF string, FD-Hessian displacements: uma_pysis.py:652-675)
+ *
+ * Conventions: plain pointers and sizes only; device pointers are owned by the caller (e.g.
+ * PyTorch tensors), `stream` is a cudaStream_t passed as void*; every function returns 0 on
+ * success, non-zero on failure with the message available from umab_last_error().  All
+ * images of one engine share one composition (atomic numbers), charge, spin and task, as one
+ * reference calculator instance does.  No CPU fallback exists: without a CUDA device every
+ * compute entry point fails.
+ */
+#ifndef UMAB_H
+#define UMAB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define UMAB_API __attribute__((visibility("default")))
+#else
+#define UMAB_API
+#endif
+
+typedef struct umab_engine umab_engine;
+
+typedef struct umab_config {
+    int32_t sphere_channels;    /* 128 (compiled in) */
+    int32_t hidden_channels;    /* 128 (compiled in) */
+    int32_t num_distance_basis; /* 64  (compiled in) */
+    int32_t num_layers;         /* 4 */
+    int32_t max_neighbors;      /* 300 */
+    int32_t device;             /* CUDA ordinal */
+    int32_t debug;              /* 1: keep named intermediates for umab_debug_tensor */
+    int32_t gemm_mode;          /* 0: fp32 SIMT, 1: tcgen05 bf16x3 tensor-core path */
+    float cutoff;               /* 6.0 Angstrom */
+    float edge_degree_rescale;  /* 5.0 */
+    int64_t workspace_bytes;    /* per-chunk edge workspace budget; 0 = default */
+} umab_config;
+
+/* ABI version of this header; umab_abi_version() must return the same value. */
+#define UMAB_ABI_VERSION 1
+
+UMAB_API int32_t umab_abi_version(void);
+UMAB_API const char* umab_last_error(void);
+
+UMAB_API int32_t umab_create(const umab_config* cfg, umab_engine** out);
+UMAB_API void umab_destroy(umab_engine* e);
+
+/* Copy one named fp32 parameter (host memory) into the engine. */
+UMAB_API int32_t umab_set_weight(umab_engine* e, const char* name, const float* host, size_t numel);
+/* Verify that every parameter the kernels need is present with the expected size. */
+UMAB_API int32_t umab_finalize_weights(umab_engine* e);
+
+/* Atomic numbers of ONE image (host, n_atoms ints); all images share them. */
+UMAB_API int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms);
+
+/* Neighbour search only: pos_dev [n_images, n_atoms, 3] fp32 on the device. */
+UMAB_API int32_t umab_build_graph(umab_engine* e, const float* pos_dev, int32_t n_images, void* stream);
+UMAB_API int32_t umab_graph_counts(umab_engine* e, int64_t* n_nodes, int64_t* n_edges);
+/* Copy the canonical (target, source)-sorted edge list out; either pointer may be NULL. */
+UMAB_API int32_t umab_graph_copy(umab_engine* e, int32_t* src_dev, int32_t* tgt_dev, int32_t* row_ptr_dev, void* stream);
+
+/* Energies [n_images] (double, eV) and forces [n_images, n_atoms, 3] (fp32, eV/A; NULL = energy
+ * only, skips the backward pass).  Device pointers.  Rebuilds the graph on every call, as the
+ * reference does.  Synchronises `stream` once internally (edge-count read-back). */
+UMAB_API int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_t n_images,
+                           double* energy_dev, float* forces_dev, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): H2D, compute, D2H and a final sync inside. */
+UMAB_API int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n_images,
+                                double* energy_host, float* forces_host, void* stream);
+
+/* Standalone GEMM  C[M,N] = A[M,K] . W[N,K]^T (+bias), device pointers, for kernel unit tests
+ * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3. */
+UMAB_API int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const float* bias_dev, float* c_dev,
+                  int64_t m, int32_t n, int32_t k, void* stream);
+
+/* Debug access (config.debug = 1): device pointer + element count of a named intermediate of
+ * the last umab_energy_forces call.  The pointer stays valid until the next call. */
+UMAB_API int32_t umab_debug_tensor(umab_engine* e, const char* name, const float** ptr_dev, size_t* numel);
+
+/* Counters since creation: kernel launches issued by this library and bytes allocated. */
+UMAB_API int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UMAB_H */

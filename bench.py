@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the uma_pysis hot path: batched UMA energy+force evaluation of a string of images.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, NCCL)
+    python bench.py --impl reference ...                      (CPU oracle = the reference arm)
+
+One "step" = one pass of the hot path over the batch: every image of the string gets its graph
+rebuilt (as the reference does on each call), its energy and its forces.  Workload = BASELINE.json
+configs[3]: a 32-image string on a 1500-atom cluster model (synthetic, deterministic), random-init
+uma-s-1p1-architecture weights.  Prints ONE JSON line (see the keys below / DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image energy+force evals/s"
+UNIT = "image-evals/s"
+FLOP_PER_EDGE_EF = 31.0e6          # energy+forces, algorithmic (recompute not counted)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--atoms", type=int, default=1500)
+    p.add_argument("--images", type=int, default=32)
+    p.add_argument("--seed", type=int, default=4)
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    p.add_argument("--gemm", default=os.environ.get("UMAB_GEMM", "auto"), choices=["auto", "simt", "tc"])
+    p.add_argument("--experts", type=int, default=32)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample-atoms", type=int, default=None)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_inputs(args, rank, world):
+    from pdb2reaction_b200 import synth
+    if args.scaling == "weak":
+        elem, imgs = synth.make_string(args.atoms, args.images, args.seed)
+        if rank:
+            rng = np.random.default_rng(1000 + rank)
+            imgs = imgs + rng.normal(scale=0.02, size=imgs.shape)      # distinct strings per rank
+        return elem, imgs, args.images * world
+    elem, imgs = synth.make_string(args.atoms, args.images, args.seed)
+    from pdb2reaction_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(args.images, world)[rank]
+    return elem, imgs[lo:hi], args.images
+
+
+def cpu_sample(elem, imgs, n_sample):
+    """Bounded CPU sample of the workload: the ``n_sample`` atoms nearest the centroid of image 0
+    (same density and composition statistics as the full image; fewer surface-free neighbours, so
+    the per-atom cost is if anything LOWER than in the full image -- favourable to the CPU)."""
+    if n_sample >= imgs.shape[1]:
+        return elem, imgs
+    c = imgs[0] - imgs[0].mean(0)
+    idx = np.sort(np.argsort((c * c).sum(1))[:n_sample])
+    return [elem[i] for i in idx], imgs[:, idx]
+
+
+def cpu_oracle(args, elem, coords_one, threads=None):
+    """The CPU restatement, reference calling pattern: one image per call, graph rebuilt, fp32."""
+    from oracle import uma_ref
+    from pdb2reaction_b200 import weights as W
+    from pdb2reaction_b200.arch import UMAArch, atomic_numbers
+    if threads:
+        torch.set_num_threads(threads)
+    arch = UMAArch(num_experts=args.experts)
+    z = atomic_numbers(elem)
+    merged = W.merge_mole(W.init_uma_weights(arch, 0), arch, z, 0, 1, "omol")
+    return uma_ref.OracleUMA(merged, z, dtype=torch.float32, hyper=uma_ref.Hyper(num_experts=args.experts),
+                             edge_chunk=16384)
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's path (the reference itself cannot be
+    installed: fairchem-core is absent), reference calling pattern, all host threads.  Each step
+    evaluates a bounded sample (a ``--cpu-sample-atoms`` sub-cluster of one image); the value is
+    converted to whole-image evaluations per second by atoms: (atoms/s) / atoms-per-image."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pdb2reaction_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    elem, imgs = synth.make_string(args.atoms, args.images, args.seed)
+    n_s = min(args.cpu_sample_atoms or 300, args.atoms)
+    elem_s, imgs_s = cpu_sample(elem, imgs, n_s)
+    orc = cpu_oracle(args, elem_s, imgs_s[0])
+    for w in range(args.warmup):
+        orc.energy_forces(imgs_s[w % len(imgs_s)])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        orc.energy_forces(imgs_s[k % len(imgs_s)])
+    dt = time.perf_counter() - t0
+    atoms_per_s = args.steps * n_s / dt
+    val = atoms_per_s / args.atoms
+    sample = (f"per step: energy+forces of a {n_s}-atom sub-cluster of one {args.atoms}-atom image (graph rebuilt, "
+              f"fp32, batch of 1, activation checkpointing); value = atoms/s / {args.atoms}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "atoms_per_s": atoms_per_s,
+        "config": {"workload": f"C4: DMF/GSM string, {args.images} images x {args.atoms} atoms (BASELINE.json configs[3])",
+                   "n_atoms": args.atoms, "n_images": args.images, "weights": "random-init uma-s-1p1 architecture, seed 0"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from pdb2reaction_b200 import calculator as calc_mod
+    from pdb2reaction_b200 import engine as engine_mod
+    from pdb2reaction_b200 import uma_pysis
+    from pdb2reaction_b200.arch import UMAArch
+    from pdb2reaction_b200.shims import ANG2BOHR
+
+    if args.gemm != "auto":
+        os.environ["UMAB_GEMM"] = args.gemm
+    elif "UMAB_GEMM" not in os.environ:
+        os.environ["UMAB_GEMM"] = engine_mod.DEFAULT_GEMM
+    gemm_name = os.environ["UMAB_GEMM"]
+    elem, imgs, total_images = build_inputs(args, rank, world)
+    n_local = imgs.shape[0]
+    arch = UMAArch(num_experts=args.experts)
+    if args.experts != 32:
+        orig = calc_mod.CudaBackend.__init__
+        calc_mod.CudaBackend.__init__ = lambda self, e, **kw: orig(self, e, **{**kw, "arch": arch})
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        calc = uma_pysis(device=f"cuda:{local}")       # the public API object (e2e path)
+        calc._ensure_core(elem)
+    eng = calc._core.backend.engines[0]
+    pos_dev = torch.from_numpy(imgs.astype(np.float32)).cuda()
+
+    def _step_impl():
+        e, f = eng.energy_forces(pos_dev)
+        if world > 1:                                   # the one collective of the path
+            from pdb2reaction_b200.sharding import pack_results
+            rec = pack_results(e, f, n_local, args.atoms)
+            out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
+            dist.all_gather_into_tensor(out, rec)
+        return e, f
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        _step_impl()
+    barrier()
+    eng.profile(True)
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        e_last, f_last = _step_impl()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats()["kernel_launches"] - launches0
+    fam = eng.profile_read()
+    eng.profile(False)
+    n_nodes, n_edges = eng.graph_counts()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_tot = t.item()
+    value = total_images * args.steps / (ms_tot / 1e3)
+
+    # ---------------- end to end through the public calculator API (`e2e`)
+    coords_bohr = (imgs * ANG2BOHR).reshape(n_local, -1)
+    for _ in range(min(2, args.warmup)):
+        calc.get_forces_batch(elem, coords_bohr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = calc.get_forces_batch(elem, coords_bohr)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = total_images * args.steps / t.item()
+    assert np.isfinite(res["energy"]).all() and np.isfinite(res["forces"]).all()
+
+    if rank == 0:
+        pk = peaks()
+        dom = max(fam, key=lambda k: fam[k]["ms"])
+        d = fam[dom]
+        per_launch_ms = d["ms"] / max(d["launches"], 1)
+        if dom == "gemm":
+            ach = d["work"] / (d["ms"] * 1e-3) / 1e12
+            # bf16x3: three bf16 MMAs per fp32-accurate product -> the effective peak is a third
+            passes = 3.0 if gemm_name == "tc" else 1.0
+            peak = pk["tf_sustained"] / passes
+            roof = {"kernel": "gemm_tc (tcgen05 bf16x3)" if gemm_name == "tc" else "gemm_simt (fp32 FFMA)",
+                    "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_source": pk["source"] + f", bf16 dense sustained / {passes:g} passes",
+                    "flops_per_launch": d["work"] / max(d["launches"], 1), "ms_per_launch": per_launch_ms,
+                    "launches": d["launches"], "share_of_step": d["ms"] / (ms * 1.0)}
+        else:
+            ach = d["work"] / (d["ms"] * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "peak_source": pk["source"],
+                    "bytes_per_launch": d["work"] / max(d["launches"], 1), "ms_per_launch": per_launch_ms,
+                    "launches": d["launches"], "share_of_step": d["ms"] / ms}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        roof["traffic"] = None
+        if os.path.exists(tpath):
+            try:
+                roof["traffic"] = json.load(open(tpath)).get(roof["kernel"].split(" ")[0])
+            except Exception:
+                pass
+        fam_out = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                       "rate": (v["work"] / (v["ms"] * 1e-3) / (1e12 if k == "gemm" else 1e9)) if v["ms"] > 0 else 0.0,
+                       "rate_unit": "TFLOP/s" if k == "gemm" else "GB/s"} for k, v in fam.items() if v["launches"]}
+        edges_per_step = n_edges
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_tot / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32" if gemm_name == "simt" else "f32 (bf16x3 split tensor-core GEMMs, fp32 accumulate)",
+            "data": "synthetic",
+            "atoms_per_s": value * args.atoms,
+            "config": {"workload": f"C4: DMF/GSM string, {args.images} images x {args.atoms} atoms per GPU-batch "
+                                   f"(BASELINE.json configs[3]); {total_images} images in the job",
+                       "n_atoms": args.atoms, "n_images_per_gpu": n_local, "edges_per_gpu_step": int(edges_per_step),
+                       "weights": f"random-init uma-s-1p1 architecture ({args.experts} experts merged), seed 0",
+                       "gemm": gemm_name, "l2": "working set (GBs of per-edge activations) >> 126 MB L2; no flush needed",
+                       "collective": "all_gather of [E|F] per step" if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_local * args.atoms * 12),
+                    "d2h_bytes_per_step": int(n_local * (8 + args.atoms * 12)),
+                    "api": "uma_pysis.get_forces_batch(elem, coords_bohr) -> host numpy (Hartree, Hartree/Bohr)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_families": fam_out,
+            "model_tflops_algorithmic": edges_per_step * FLOP_PER_EDGE_EF * world / (ms_tot / args.steps * 1e-3) / 1e12,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_s = min(args.cpu_sample_atoms or 300, args.atoms)
+            elem_s, imgs_s = cpu_sample(elem, imgs, n_s)
+            orc = cpu_oracle(args, elem_s, imgs_s[0], threads=cores)
+            orc.energy_forces(imgs_s[0])          # warm-up (thread pools, allocator)
+            t0 = time.perf_counter()
+            reps = 2
+            for k in range(reps):
+                orc.energy_forces(imgs_s[k % len(imgs_s)])
+            dtc = (time.perf_counter() - t0) / reps
+            out["cpu_baseline"] = {"value": n_s / dtc / args.atoms, "unit": UNIT, "cores": torch.get_num_threads(),
+                                   "kind": "port",
+                                   "sample": f"energy+forces of a {n_s}-atom sub-cluster of one image, oracle fp32, "
+                                             f"graph rebuilt, {dtc:.1f} s per evaluation; value = atoms/s / {args.atoms}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,14 @@ UMAB_API int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev,
  * the last umab_energy_forces call.  The pointer stays valid until the next call. */
 UMAB_API int32_t umab_debug_tensor(umab_engine* e, const char* name, const float** ptr_dev, size_t* numel);
 
+/* Per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline):
+ * enable (resets the counters) / disable; read the accumulated device milliseconds, launch count
+ * and algorithmic work (FLOPs for "gemm", bytes otherwise) of family `cat`;
+ * umab_profile_name(cat) is NULL past the last family. */
+UMAB_API int32_t umab_profile(umab_engine* e, int32_t enable);
+UMAB_API int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work);
+UMAB_API const char* umab_profile_name(int32_t cat);
+
 /* Counters since creation: kernel launches issued by this library and bytes allocated. */
 UMAB_API int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_bytes);
 

@@ -132,20 +132,31 @@ def so3_linear(x, weight, bias):
 
 
 # ------------------------------------------------------------------ blocks
+def _edge_chunk_messages(w, p, x, x_edge, src, tgt, wig_m, wig_m_inv_env, hp, coeff):
+    msg = torch.cat([x[src], x[tgt]], dim=2)
+    msg = torch.bmm(wig_m, msg)
+    rad = radial_mlp(w, p + ".edge.conv1.rad", x_edge)
+    msg, gate = so2_conv(w, p + ".edge.conv1", msg, rad, 2 * hp.C, hp.H, 2 * hp.H, coeff)
+    msg = gate_act(gate, msg, GATE_IDX_M, hp.H)
+    msg, _ = so2_conv(w, p + ".edge.conv2", msg, None, hp.H, hp.C, 0, coeff)
+    return torch.bmm(wig_m_inv_env, msg)
+
+
 def edgewise(w, p, x, x_edge, src, tgt, wig_m, wig_m_inv_env, hp, coeff, edge_chunk=None):
+    """Edgewise block.  With ``edge_chunk`` the edges are processed in chunks under activation
+    checkpointing (fairchem's default inference setting), bounding autograd memory."""
     n = x.shape[0]
     out = x.new_zeros(n, 9, hp.C)
     e_tot = src.shape[0]
     step = e_tot if not edge_chunk else int(edge_chunk)
     for s in range(0, max(e_tot, 1), max(step, 1)):
         sl = slice(s, min(e_tot, s + step))
-        msg = torch.cat([x[src[sl]], x[tgt[sl]]], dim=2)
-        msg = torch.bmm(wig_m[sl], msg)
-        rad = radial_mlp(w, p + ".edge.conv1.rad", x_edge[sl])
-        msg, gate = so2_conv(w, p + ".edge.conv1", msg, rad, 2 * hp.C, hp.H, 2 * hp.H, coeff)
-        msg = gate_act(gate, msg, GATE_IDX_M, hp.H)
-        msg, _ = so2_conv(w, p + ".edge.conv2", msg, None, hp.H, hp.C, 0, coeff)
-        msg = torch.bmm(wig_m_inv_env[sl], msg)
+        args = (x, x_edge[sl], src[sl], tgt[sl], wig_m[sl], wig_m_inv_env[sl])
+        if edge_chunk and torch.is_grad_enabled() and x.requires_grad:
+            from torch.utils.checkpoint import checkpoint
+            msg = checkpoint(lambda *a: _edge_chunk_messages(w, p, *a, hp, coeff), *args, use_reentrant=False)
+        else:
+            msg = _edge_chunk_messages(w, p, *args, hp, coeff)
         out = out.index_add(0, tgt[sl], msg)
     return out
 

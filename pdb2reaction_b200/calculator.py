@@ -1,0 +1,358 @@
+"""Drop-in ``uma_pysis`` calculator backed by the batched B200 engine.
+
+Mirrors the public surface of the reference's ``pdb2reaction/uma_pysis.py`` (file:line cited at
+each method): keyword-only constructor with the 15 ``CALC_KW`` keys (+ ``**kwargs`` to the
+pysisyphus base, ``:432-499``), ``get_energy`` / ``get_forces`` / ``get_hessian`` taking element
+symbols and flat Bohr coordinates and returning Hartree / Hartree Bohr^-1 / Hartree Bohr^-2
+(``:689-780``), freeze-atom handling (``:554-592``), finite-difference Hessian with h = 1e-3 A
+over active DOF only (``:595-686``) and the symmetrise / scale / cast / torch-or-numpy formatting of
+``_au_hessian`` (``:515-551``).
+
+What changes underneath: every evaluation is a *batch*.  ``get_energy_batch`` /
+``get_forces_batch`` evaluate all images of a string in one engine call, and the FD Hessian
+evaluates its 2 x 3 N_active displaced geometries as batches instead of one ``predict`` per
+displacement.  ``workers`` keeps its name and becomes "number of GPUs of this box to shard the
+batch over" (images / displacements are independent; each GPU holds a replica of the merged
+weights), driven from host threads inside this one process.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import warnings
+from concurrent.futures import ThreadPoolExecutor
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .arch import UMAArch, atomic_numbers
+from .shims import Calculator, BOHR2ANG, ANG2BOHR, AU2EV
+from . import weights as _weights
+
+# ------------ unit conversion constants (reference uma_pysis.py:127-129) ----------------
+EV2AU = 1.0 / AU2EV
+F_EVAA_2_AU = EV2AU / ANG2BOHR
+H_EVAA_2_AU = EV2AU / ANG2BOHR / ANG2BOHR
+
+GEOM_KW_DEFAULT: Dict[str, Any] = {"coord_type": "cart", "freeze_atoms": []}
+
+# same keys and defaults as the reference (uma_pysis.py:138-165)
+CALC_KW: Dict[str, Any] = {
+    "charge": 0,
+    "spin": 1,
+    "model": "uma-s-1p1",
+    "task_name": "omol",
+    "device": "auto",
+    "workers": 1,
+    "workers_per_node": 1,
+    "max_neigh": None,
+    "radius": None,
+    "r_edges": False,
+    "out_hess_torch": True,
+    "freeze_atoms": None,
+    "hessian_calc_mode": "FiniteDifference",
+    "return_partial_hessian": False,
+    "hessian_double": True,
+}
+
+FD_STEP_ANG = 1.0e-3            # reference uma_pysis.py:600
+MAX_ATOMS_PER_CALL = 49152      # node-state memory bound of one engine call (~100 KB / atom)
+
+
+# ======================================================================================
+# weights: process-wide cache (the reference re-creates calculators constantly)
+# ======================================================================================
+_state_lock = threading.Lock()
+_state_cache: Dict[str, Dict[str, torch.Tensor]] = {}
+_engine_cache: Dict[tuple, Any] = {}
+
+
+def load_model_state(model: str, arch: UMAArch) -> Dict[str, torch.Tensor]:
+    """Un-merged state dict for ``model``.
+
+    ``model`` is either a path to a ``torch.save``d state dict in this package's naming
+    (``weights.init_uma_weights``) or a model ID such as ``"uma-s-1p1"``.  The reference downloads
+    the ID from a gated HF repo (``uma_pysis.py:246-250``); offline that is impossible, so an ID
+    resolves to ``$UMAB_WEIGHTS`` if set, else to RANDOM-INIT weights of the uma-s-1p1
+    architecture (seed 0) with a warning -- energies are then not physical.
+    """
+    path = model if os.path.exists(str(model)) else os.environ.get("UMAB_WEIGHTS")
+    key = f"file:{path}" if path else f"random:{model}:{arch.num_experts}"
+    with _state_lock:
+        if key not in _state_cache:
+            if path:
+                _state_cache[key] = torch.load(path, map_location="cpu")
+            else:
+                warnings.warn(
+                    f"no checkpoint available for model {model!r} (offline): using random-init "
+                    "uma-s-1p1-architecture weights, seed 0", RuntimeWarning, stacklevel=3)
+                _state_cache[key] = _weights.init_uma_weights(arch, seed=0)
+        return _state_cache[key]
+
+
+class CudaBackend:
+    """Engines on ``workers`` GPUs; a batch of images is split into contiguous shards."""
+
+    def __init__(self, elem: Sequence[str], *, charge, spin, model, task_name, device, workers, max_neigh,
+                 radius, arch: Optional[UMAArch] = None):
+        from .engine import UmabEngine  # raises if the extension is missing
+        if device in ("auto", None):
+            device = "cuda"
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"device={device!r}: pdb2reaction_b200 has no CPU path (B200-native backend); "
+                "use device='cuda'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: pdb2reaction_b200 has no CPU fallback")
+        self.arch = arch or UMAArch()
+        self.z = atomic_numbers(elem)
+        first = dev.index if dev.index is not None else torch.cuda.current_device()
+        n_gpu = torch.cuda.device_count()
+        workers = max(1, int(workers or 1))
+        if first + workers > n_gpu:
+            raise RuntimeError(f"workers={workers} requested from cuda:{first} but only {n_gpu} GPUs are visible")
+        self.devices = list(range(first, first + workers))
+        self.torch_device = torch.device("cuda", first)
+        key_base = (str(model), tuple(self.z), int(charge), int(spin), str(task_name),
+                    None if radius is None else float(radius), None if max_neigh is None else int(max_neigh))
+        self.engines = []
+        for d in self.devices:
+            key = key_base + (d,)
+            with _state_lock:
+                eng = _engine_cache.get(key)
+            if eng is None:
+                state = load_model_state(model, self.arch)
+                merged = _weights.merge_mole(state, self.arch, self.z, charge, spin, task_name)
+                eng = UmabEngine(merged, self.z, self.arch, device=d, cutoff=radius, max_neighbors=max_neigh)
+                with _state_lock:
+                    _engine_cache[key] = eng
+            self.engines.append(eng)
+        self._pool = ThreadPoolExecutor(max_workers=len(self.engines)) if len(self.engines) > 1 else None
+
+    def evaluate(self, coords_ang: np.ndarray, forces: bool = True):
+        """coords [B,N,3] float64 A -> (E [B] float64 eV, F [B,N,3] float32 eV/A | None)."""
+        pos = np.ascontiguousarray(coords_ang, dtype=np.float32)   # the model sees fp32 positions (Q3)
+        b, n = pos.shape[0], pos.shape[1]
+        per_call = max(1, MAX_ATOMS_PER_CALL // n)
+        e_out = np.empty(b, dtype=np.float64)
+        f_out = np.empty((b, n, 3), dtype=np.float32) if forces else None
+        from .sharding import shard_bounds
+        bounds = shard_bounds(b, len(self.engines))
+
+        def run(rank):
+            lo, hi = bounds[rank]
+            for s in range(lo, hi, per_call):
+                t = min(hi, s + per_call)
+                e, f = self.engines[rank].energy_forces_host(pos[s:t], forces)
+                e_out[s:t] = e
+                if forces:
+                    f_out[s:t] = f
+
+        if self._pool is None:
+            run(0)
+        else:
+            list(self._pool.map(run, range(len(self.engines))))
+        return e_out, f_out
+
+
+# ======================================================================================
+class UMAcore:
+    """Batched counterpart of the reference's ``UMAcore`` (uma_pysis.py:170-419)."""
+
+    def __init__(self, elem: Sequence[str], *, charge=0, spin=1, model="uma-s-1p1", task_name="omol",
+                 device="auto", workers=1, workers_per_node=1, max_neigh=None, radius=None, r_edges=False,
+                 backend=None):
+        self.elem = [str(e).capitalize() for e in elem]
+        self.charge, self.spin, self.task_name = charge, spin, task_name
+        self.workers = max(1, int(workers) if workers is not None else 1)
+        self.workers_per_node = max(1, int(workers_per_node) if workers_per_node is not None else 1)
+        self.backend = backend if backend is not None else CudaBackend(
+            self.elem, charge=charge, spin=spin, model=model, task_name=task_name, device=device,
+            workers=self.workers, max_neigh=max_neigh, radius=radius)
+        self.device = getattr(self.backend, "torch_device", torch.device("cpu"))
+
+    def compute_batch(self, coords_ang: np.ndarray, *, forces: bool = False):
+        """coords [B,N,3] A -> {"energy": np.float64 [B] eV, "forces": np.float32 [B,N,3] | None}."""
+        c = np.asarray(coords_ang, dtype=np.float64)
+        if c.ndim == 2:
+            c = c[None]
+        if c.shape[1] != len(self.elem):
+            raise ValueError(f"coords hold {c.shape[1]} atoms, calculator was built for {len(self.elem)}")
+        e, f = self.backend.evaluate(c, forces=forces)
+        return {"energy": e, "forces": f}
+
+    def compute(self, coord_ang: np.ndarray, *, forces: bool = False, hessian: bool = False):
+        if hessian:
+            raise RuntimeError("Analytical Hessian is evaluated by the calculator, not by UMAcore.compute")
+        r = self.compute_batch(np.asarray(coord_ang, dtype=np.float64).reshape(1, -1, 3), forces=forces)
+        # the reference widens an fp32 energy (uma_pysis.py:387); here it was accumulated in fp64
+        return {"energy": float(r["energy"][0]), "forces": None if r["forces"] is None else r["forces"][0],
+                "hessian": None}
+
+
+class uma_pysis(Calculator):
+    """PySisyphus-compatible UMA calculator, B200 backend (reference uma_pysis.py:425-780)."""
+
+    implemented_properties = ["energy", "forces", "hessian"]
+
+    def __init__(self, *, charge: int = CALC_KW["charge"], spin: int = CALC_KW["spin"],
+                 model: str = CALC_KW["model"], task_name: str = CALC_KW["task_name"],
+                 device: str = CALC_KW["device"], workers: int = CALC_KW["workers"],
+                 workers_per_node: int = CALC_KW["workers_per_node"],
+                 out_hess_torch: bool = CALC_KW["out_hess_torch"],
+                 max_neigh: Optional[int] = CALC_KW["max_neigh"], radius: Optional[float] = CALC_KW["radius"],
+                 r_edges: bool = CALC_KW["r_edges"], freeze_atoms: Optional[Sequence[int]] = CALC_KW["freeze_atoms"],
+                 hessian_calc_mode: str = CALC_KW["hessian_calc_mode"],
+                 return_partial_hessian: bool = CALC_KW["return_partial_hessian"],
+                 hessian_double: bool = CALC_KW["hessian_double"], **kwargs):
+        backend = kwargs.pop("_backend", None)          # test hook: inject an evaluator
+        super().__init__(charge=charge, mult=spin, **kwargs)
+        self._core: Optional[UMAcore] = None
+        self._core_kw = dict(charge=charge, spin=spin, model=model, task_name=task_name, device=device,
+                             workers=workers, workers_per_node=workers_per_node, max_neigh=max_neigh,
+                             radius=radius, r_edges=r_edges, backend=backend)
+        self.out_hess_torch = out_hess_torch
+        self.hessian_calc_mode = hessian_calc_mode
+        self.freeze_atoms: List[int] = sorted(set(int(i) for i in (freeze_atoms or [])))
+        self.return_partial_hessian = bool(return_partial_hessian)
+        self.hessian_double = bool(hessian_double)
+        self._warned_analytic = False
+
+    # ---------- helpers ---------------------------------------------------------------
+    def _ensure_core(self, elem: Sequence[str]):
+        # element list / charge / spin are latched on the first call (reference :502-504, Q4)
+        if self._core is None:
+            self._core = UMAcore(elem, **self._core_kw)
+
+    @staticmethod
+    def _au_energy(e: float) -> float:
+        return e * EV2AU
+
+    @staticmethod
+    def _au_forces(f: np.ndarray) -> np.ndarray:
+        return (np.asarray(f, dtype=np.float64) * F_EVAA_2_AU).reshape(-1)
+
+    def _au_hessian(self, h: torch.Tensor):
+        """(N,3,N,3) eV/A^2 -> symmetrised [3N,3N] Hartree/Bohr^2 (reference :515-551)."""
+        n = h.size(0)
+        h = h.reshape(n * 3, n * 3)
+        h = 0.5 * (h + h.T)
+        h = h * H_EVAA_2_AU
+        if self.hessian_double:
+            h = h.to(dtype=torch.float64)
+        return h.detach() if self.out_hess_torch else h.detach().cpu().numpy()
+
+    def _active_and_frozen_dof_idx(self, n_atoms: int):
+        frozen = set(self.freeze_atoms)
+        active_atoms = [i for i in range(n_atoms) if i not in frozen]
+        active_dof = [3 * i + j for i in active_atoms for j in range(3)]
+        frozen_dof = [3 * i + j for i in self.freeze_atoms for j in range(3)]
+        return active_atoms, active_dof, frozen_dof
+
+    def _zero_frozen_forces_ev(self, f: Optional[np.ndarray]):
+        """Forces on frozen atoms are exactly 0 (reference :561-567); works on [N,3] or [B,N,3]."""
+        if f is None or not self.freeze_atoms:
+            return f
+        fz = f.copy()
+        fz[..., np.asarray(self.freeze_atoms, dtype=int), :] = 0.0
+        return fz
+
+    def _coords_ang(self, coords, batch=False):
+        c = np.asarray(coords, dtype=np.float64)
+        n = len(self._core.elem)
+        return (c.reshape(-1, n, 3) if batch else c.reshape(-1, 3)) * BOHR2ANG
+
+    # ---------- finite-difference Hessian, batched (reference :595-686) ---------------
+    def _build_fd_hessian(self, coord_ang: np.ndarray, eps_ang: float = FD_STEP_ANG):
+        core = self._core
+        dev = core.device
+        n_atoms = coord_ang.shape[0]
+        dof = 3 * n_atoms
+        active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
+        res0 = core.compute(coord_ang, forces=True)
+        f0 = res0["forces"]
+        hdt = torch.float64 if self.hessian_double else torch.float32
+        hmat = torch.zeros((dof, dof), device=dev, dtype=hdt)
+        # all +h / -h geometries, displaced in float64 before the fp32 cast (Q3)
+        per = max(1, MAX_ATOMS_PER_CALL // n_atoms) * len(getattr(core.backend, "engines", [0]))
+        per = max(2, per - per % 2)
+        for s in range(0, len(active_dof), per // 2):
+            ks = active_dof[s:s + per // 2]
+            batch = np.repeat(coord_ang[None], 2 * len(ks), axis=0)
+            for q, k in enumerate(ks):
+                a, c = divmod(k, 3)
+                batch[2 * q, a, c] = coord_ang[a, c] + eps_ang
+                batch[2 * q + 1, a, c] = coord_ang[a, c] - eps_ang
+            f = core.compute_batch(batch, forces=True)["forces"].reshape(2 * len(ks), dof)
+            ft = torch.from_numpy(f).to(dev, dtype=hdt)
+            cols = -(ft[0::2] - ft[1::2]) / (2.0 * eps_ang)                 # [len(ks), dof]
+            hmat[:, torch.as_tensor(ks, device=dev, dtype=torch.long)] = cols.T
+        if self.return_partial_hessian:
+            idx = torch.as_tensor(active_dof, device=dev, dtype=torch.long)
+            hmat = hmat.index_select(0, idx).index_select(1, idx)
+            na = len(active_atoms)
+            hmat = hmat.view(na, 3, na, 3)
+        else:
+            hmat = hmat.view(n_atoms, 3, n_atoms, 3)
+        return {"energy": res0["energy"], "forces": f0, "hessian": hmat}
+
+    # ---------- pysisyphus API ---------------------------------------------------------
+    def get_energy(self, elem, coords):
+        """reference :689-693 (energy only: the backward pass is skipped, Q1)."""
+        self._ensure_core(elem)
+        res = self._core.compute(self._coords_ang(coords), forces=False)
+        return {"energy": self._au_energy(res["energy"])}
+
+    def get_forces(self, elem, coords):
+        """reference :695-706."""
+        self._ensure_core(elem)
+        res = self._core.compute(self._coords_ang(coords), forces=True)
+        f_ev = self._zero_frozen_forces_ev(res["forces"])
+        return {"energy": self._au_energy(res["energy"]), "forces": self._au_forces(f_ev)}
+
+    def get_hessian(self, elem, coords):
+        """reference :708-780.  ``hessian_calc_mode``: anything but "analytical"/"analytic" means
+        FiniteDifference (Q8).  The analytic mode is currently served by the same batched
+        central-difference columns (second-order accurate, h = 1e-3 A) with a one-time warning;
+        hand-written HVP kernels are the planned replacement."""
+        self._ensure_core(elem)
+        coord_ang = self._coords_ang(coords)
+        mode = (self.hessian_calc_mode or "FiniteDifference").strip().lower()
+        if mode in ("analytical", "analytic") and not self._warned_analytic:
+            warnings.warn("hessian_calc_mode='Analytical': the B200 backend evaluates Hessian columns by "
+                          "batched central differences of analytic forces", RuntimeWarning, stacklevel=2)
+            self._warned_analytic = True
+        try:
+            res = self._build_fd_hessian(coord_ang)
+        except torch.cuda.OutOfMemoryError as e:
+            raise RuntimeError(
+                "Hessian computation failed due to CUDA out-of-memory. Reduce the batch by lowering "
+                "pdb2reaction_b200.calculator.MAX_ATOMS_PER_CALL.") from e
+        f_ev = self._zero_frozen_forces_ev(res["forces"])
+        return {"energy": self._au_energy(res["energy"]), "forces": self._au_forces(f_ev),
+                "hessian": self._au_hessian(res["hessian"])}
+
+    # ---------- batched extensions ----------------------------------
+    def get_energy_batch(self, elem, coords_batch):
+        """coords [B, 3N] Bohr -> {"energy": np.float64 [B] Hartree}; one engine call."""
+        self._ensure_core(elem)
+        res = self._core.compute_batch(self._coords_ang(coords_batch, batch=True), forces=False)
+        return {"energy": res["energy"] * EV2AU}
+
+    def get_forces_batch(self, elem, coords_batch):
+        """coords [B, 3N] Bohr -> {"energy": [B] Hartree, "forces": np.float64 [B, 3N] Hartree/Bohr}."""
+        self._ensure_core(elem)
+        res = self._core.compute_batch(self._coords_ang(coords_batch, batch=True), forces=True)
+        f_ev = self._zero_frozen_forces_ev(res["forces"])
+        b = f_ev.shape[0]
+        return {"energy": res["energy"] * EV2AU,
+                "forces": (np.asarray(f_ev, dtype=np.float64) * F_EVAA_2_AU).reshape(b, -1)}
+
+
+def run_pysis():
+    """Enable ``uma_pysis input.yaml`` (reference :784-789); needs a real pysisyphus."""
+    from pysisyphus import run  # type: ignore
+    run.CALC_DICT["uma_pysis"] = uma_pysis
+    run.run()

@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for log in logs:
             sys.stderr.write(log)
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
         run(cmd)
     return LIB
 

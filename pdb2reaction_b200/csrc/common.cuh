@@ -1,6 +1,7 @@
 // Shared device/host helpers for the umab sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -32,7 +33,7 @@ inline void check_cuda(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define UMAB_CUDA(x) ::umab::check_cuda((x), #x, __FILE__, __LINE__)
-extern long long g_launch_count;   // kernels launched by this library (defined in engine.cu)
+extern std::atomic<long long> g_launch_count;   // kernels launched by this library (defined in engine.cu)
 #define UMAB_LAUNCH_CHECK() (++::umab::g_launch_count, ::umab::check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__))
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

@@ -9,6 +9,7 @@
 // recomputes them chunk by chunk (chunks = contiguous target-node ranges of the CSR), so the
 // edge workspace is bounded by `workspace_bytes` regardless of batch size.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -21,7 +22,7 @@
 
 namespace umab {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 void gemm_tc(const GemmArgs& a, cudaStream_t st);   // gemm_tc.cu
 bool gemm_tc_supported(const GemmArgs& a);
 
@@ -77,6 +78,35 @@ struct LayerW {
     const float *smlp, *smlp_t, *smlp_b, *so3_1, *so3_1_t, *so3_1_b, *so3_2, *so3_2_t, *so3_2_b;
 };
 
+// ---- per-kernel-family timing with CUDA events on the launching stream (bench.py roofline)
+enum ProfCat { P_GEMM = 0, P_GATHER, P_GATHER_BWD, P_COMBINE, P_COMBINE_BWD, P_ROTBACK, P_ROTBACK_BWD,
+               P_SRC_REDUCE, P_LN_SILU, P_NODE, P_GRAPH, P_GEOMETRY, P_COUNT };
+const char* const kProfNames[P_COUNT] = {"gemm", "gather_rotate_scale", "gather_rotate_bwd", "combine_gate_fwd",
+                                         "combine_gate_bwd", "rotate_back_reduce", "rotate_back_bwd",
+                                         "source_reduce", "ln_silu", "node_ops", "graph", "geometry"};
+struct Prof {
+    bool on = false;
+    struct Rec { int cat; cudaEvent_t a, b; double work; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[P_COUNT] = {0}; double work[P_COUNT] = {0}; long long n[P_COUNT] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; UMAB_CUDA(cudaEventCreate(&e)); return e;
+    }
+    void collect() {
+        for (auto& r : recs) {
+            UMAB_CUDA(cudaEventSynchronize(r.b));
+            float t = 0.f;
+            UMAB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+            ms[r.cat] += t; work[r.cat] += r.work; n[r.cat] += 1;
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    void reset() { collect(); for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; work[i] = 0; n[i] = 0; } }
+};
+
 constexpr size_t EDGE_WS_FLOATS = 2304 + 2176 + 1152 + 1920 + 1536 + 4 * 128;   // 9600 per edge
 
 }  // namespace
@@ -118,6 +148,18 @@ struct umab_engine {
     DevBuf e_dev, f_dev;
     // debug
     std::map<std::string, std::pair<DevBuf, size_t>> dbg;
+    // profiling + pinned host staging
+    Prof prof;
+    void* hp_pos = nullptr; void* hp_f = nullptr; void* hp_e = nullptr; size_t hp_cap = 0, hp_ecap = 0;
+
+    template <class F> void timed(int cat, double work, cudaStream_t st, F&& f) {
+        if (!prof.on) { f(); return; }
+        Prof::Rec r{cat, prof.get(), prof.get(), work};
+        UMAB_CUDA(cudaEventRecord(r.a, st));
+        f();
+        UMAB_CUDA(cudaEventRecord(r.b, st));
+        prof.recs.push_back(r);
+    }
 
     const float* W(const std::string& name, size_t numel) {
         auto it = weights.find(name);
@@ -179,8 +221,10 @@ struct umab_engine {
 
     // ------------------------------------------------------------------ helpers
     void gemm(const GemmArgs& a, cudaStream_t st) {
-        if (cfg.gemm_mode == 1 && gemm_tc_supported(a)) gemm_tc(a, st);
-        else gemm_simt(a, st);
+        timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
+            if (cfg.gemm_mode == 1 && gemm_tc_supported(a)) gemm_tc(a, st);
+            else gemm_simt(a, st);
+        });
     }
     void mm(const float* A, long long lda, const float* Wt, int N, int K, float* Cm, long long ldc, long long M,
             const float* bias, int accumulate, cudaStream_t st) {
@@ -300,11 +344,12 @@ struct umab_engine {
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)
     void edge_fwd_chunk(const LayerW& w, const float* n1, const Chunk& c, int layer, bool dbg_on, cudaStream_t st) {
         radial_fwd(w.rad, c, st);
-        launch_gather_rotate_scale(n1, src.i(), tgt.i(), wig.f(), wRAD.f(), c.e0, c.n_e, A0(), A1(), A2(), st);
+        timed(P_GATHER, c.n_e * 15512.0 + c.n_nodes * 4608.0, st, [&] {
+            launch_gather_rotate_scale(n1, src.i(), tgt.i(), wig.f(), wRAD.f(), c.e0, c.n_e, A0(), A1(), A2(), st); });
         mm(A0(), 768, w.c1m0, 640, 768, Y0(), 640, c.n_e, w.c1m0_b, 0, st);
         mm(A1(), 512, w.c1m1, 512, 512, Y1(), 512, 2LL * c.n_e, nullptr, 0, st);
         mm(A2(), 256, w.c1m2, 256, 256, Y2(), 256, 2LL * c.n_e, nullptr, 0, st);
-        launch_combine_gate_fwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), st);
+        timed(P_COMBINE, c.n_e * 13312.0, st, [&] { launch_combine_gate_fwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), st); });
         mm(B0(), 384, w.c2m0, 384, 384, Z0(), 384, c.n_e, w.c2m0_b, 0, st);
         mm(B1(), 256, w.c2m1, 512, 256, Z1(), 512, 2LL * c.n_e, nullptr, 0, st);
         mm(B2(), 128, w.c2m2, 256, 128, Z2(), 256, 2LL * c.n_e, nullptr, 0, st);
@@ -324,17 +369,20 @@ struct umab_engine {
     }
     void edge_bwd_chunk(const LayerW& w, const float* n1, const Chunk& c, const float* g_out, float* g_n1, cudaStream_t st) {
         edge_fwd_chunk(w, n1, c, -1, false, st);
-        launch_rotate_back_bwd(0, Z0(), Z1(), Z2(), tgt.i(), wig.f(), env.f(), 1.0f, c.e0, c.n_e, g_out,
-                               Z0(), Z1(), Z2(), g_env.f(), g_wig.f(), st);
+        timed(P_ROTBACK_BWD, c.n_e * (2 * 7680.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0, st, [&] {
+            launch_rotate_back_bwd(0, Z0(), Z1(), Z2(), tgt.i(), wig.f(), env.f(), 1.0f, c.e0, c.n_e, g_out,
+                                   Z0(), Z1(), Z2(), g_env.f(), g_wig.f(), st); });
         mm(Z0(), 384, w.c2m0_t, 384, 384, B0(), 384, c.n_e, nullptr, 0, st);
         mm(Z1(), 512, w.c2m1_t, 256, 512, B1(), 256, 2LL * c.n_e, nullptr, 0, st);
         mm(Z2(), 256, w.c2m2_t, 128, 256, B2(), 128, 2LL * c.n_e, nullptr, 0, st);
-        launch_combine_gate_bwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), Y0(), Y1(), Y2(), st);
+        timed(P_COMBINE_BWD, c.n_e * (8704.0 * 2 + 4608.0), st, [&] {
+            launch_combine_gate_bwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), Y0(), Y1(), Y2(), st); });
         mm(Y0(), 640, w.c1m0_t, 768, 640, A0(), 768, c.n_e, nullptr, 0, st);
         mm(Y1(), 512, w.c1m1_t, 512, 512, A1(), 512, 2LL * c.n_e, nullptr, 0, st);
         mm(Y2(), 256, w.c1m2_t, 256, 256, A2(), 256, 2LL * c.n_e, nullptr, 0, st);
-        launch_gather_rotate_bwd(n1, row_ptr.i(), src.i(), wig.f(), wRAD.f(), c.e0, c.node0, c.n_nodes, A0(), A1(), A2(),
-                                 wRAD.f(), Gbuf.f(), g_n1, g_wig.f(), st);
+        timed(P_GATHER_BWD, c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0, st, [&] {
+            launch_gather_rotate_bwd(n1, row_ptr.i(), src.i(), wig.f(), wRAD.f(), c.e0, c.node0, c.n_nodes, A0(), A1(), A2(),
+                                     wRAD.f(), Gbuf.f(), g_n1, g_wig.f(), st); });
         radial_bwd(w.rad, c, st);
     }
 
@@ -376,8 +424,9 @@ struct umab_engine {
             save_dbg("l" + std::to_string(l) + ".n1", nbuf.p, (size_t)n_nodes * 9 * C, st);
             for (const Chunk& c : chunks) {
                 edge_fwd_chunk(w, nbuf.f(), c, l, true, st);
-                launch_rotate_back_reduce(0, Z0(), Z1(), Z2(), row_ptr.i(), wig.f(), env.f(), 1.0f, c.e0, c.node0,
-                                          c.n_nodes, xs[l].f(), x1s[l].f(), st);
+                timed(P_ROTBACK, c.n_e * 7828.0 + c.n_nodes * 9216.0, st, [&] {
+                    launch_rotate_back_reduce(0, Z0(), Z1(), Z2(), row_ptr.i(), wig.f(), env.f(), 1.0f, c.e0, c.node0,
+                                              c.n_nodes, xs[l].f(), x1s[l].f(), st); });
             }
             save_dbg("l" + std::to_string(l) + ".x1", x1s[l].p, (size_t)n_nodes * 9 * C, st);
             launch_rms_fwd(x1s[l].f(), w.n2w, w.n2b, nullptr, n_nodes, nbuf.f(), st);
@@ -424,7 +473,8 @@ struct umab_engine {
             // Edgewise adjoint
             launch_rms_fwd(xs[l].f(), w.n1w, w.n1b, csd, n_nodes, nbuf.f(), st);       // recompute n1
             for (const Chunk& c : chunks) edge_bwd_chunk(w, nbuf.f(), c, gx1.f(), gn.f(), st);
-            launch_source_reduce(Gbuf.f(), sptr.i(), sedge.i(), n_nodes, gn.f(), st);
+            timed(P_SRC_REDUCE, n_edges * 4612.0 + n_nodes * 9216.0, st, [&] {
+                launch_source_reduce(Gbuf.f(), sptr.i(), sedge.i(), n_nodes, gn.f(), st); });
             save_dbg("l" + std::to_string(l) + ".g_n1", gn.p, (size_t)n_nodes * 9 * C, st);
             launch_rms_bwd(xs[l].f(), w.n1w, gn.f(), gx1.f(), n_nodes, gx.f(), st);    // g_x_l
             save_dbg("l" + std::to_string(l) + ".g_x", gx.p, (size_t)n_nodes * 9 * C, st);
@@ -456,6 +506,11 @@ struct umab_engine {
         for (auto* v : {&xs, &x1s, &y1s, &gps}) for (auto& b : *v) b.release();
         for (auto& kv : dbg) kv.second.first.release();
         if (h_pinned) cudaFreeHost(h_pinned);
+        if (hp_pos) cudaFreeHost(hp_pos);
+        if (hp_f) cudaFreeHost(hp_f);
+        if (hp_e) cudaFreeHost(hp_e);
+        prof.collect();
+        for (auto ev : prof.pool) cudaEventDestroy(ev);
     }
 };
 
@@ -574,11 +629,27 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
     e->pos_own.ensure(nb);
     e->e_dev.ensure(sizeof(double) * n_images);
     if (forces_host) e->f_dev.ensure(nb);
-    UMAB_CUDA(cudaMemcpyAsync(e->pos_own.p, pos_host, nb, cudaMemcpyHostToDevice, st));
+    // pinned staging on both sides so the copies are true async DMA transfers
+    if (nb > e->hp_cap) {
+        if (e->hp_pos) cudaFreeHost(e->hp_pos);
+        if (e->hp_f) cudaFreeHost(e->hp_f);
+        UMAB_CUDA(cudaMallocHost(&e->hp_pos, nb + nb / 4));
+        UMAB_CUDA(cudaMallocHost(&e->hp_f, nb + nb / 4));
+        e->hp_cap = nb + nb / 4;
+    }
+    if (sizeof(double) * n_images > e->hp_ecap) {
+        if (e->hp_e) cudaFreeHost(e->hp_e);
+        UMAB_CUDA(cudaMallocHost(&e->hp_e, sizeof(double) * n_images * 2));
+        e->hp_ecap = sizeof(double) * n_images * 2;
+    }
+    memcpy(e->hp_pos, pos_host, nb);
+    UMAB_CUDA(cudaMemcpyAsync(e->pos_own.p, e->hp_pos, nb, cudaMemcpyHostToDevice, st));
     e->evaluate(e->pos_own.f(), n_images, e->e_dev.as<double>(), forces_host ? e->f_dev.f() : nullptr, st);
-    UMAB_CUDA(cudaMemcpyAsync(energy_host, e->e_dev.p, sizeof(double) * n_images, cudaMemcpyDeviceToHost, st));
-    if (forces_host) UMAB_CUDA(cudaMemcpyAsync(forces_host, e->f_dev.p, nb, cudaMemcpyDeviceToHost, st));
+    UMAB_CUDA(cudaMemcpyAsync(e->hp_e, e->e_dev.p, sizeof(double) * n_images, cudaMemcpyDeviceToHost, st));
+    if (forces_host) UMAB_CUDA(cudaMemcpyAsync(e->hp_f, e->f_dev.p, nb, cudaMemcpyDeviceToHost, st));
     UMAB_CUDA(cudaStreamSynchronize(st));
+    memcpy(energy_host, e->hp_e, sizeof(double) * n_images);
+    if (forces_host) memcpy(forces_host, e->hp_f, nb);
     UMAB_CATCH
 }
 
@@ -607,10 +678,30 @@ int32_t umab_debug_tensor(umab_engine* e, const char* name, const float** ptr_de
     UMAB_CATCH
 }
 
+int32_t umab_profile(umab_engine* e, int32_t enable) {
+    UMAB_TRY
+    if (!e) throw CudaError("null argument");
+    e->prof.reset();
+    e->prof.on = enable != 0;
+    UMAB_CATCH
+}
+
+int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work) {
+    UMAB_TRY
+    if (!e || cat < 0 || cat >= P_COUNT) throw CudaError("bad argument");
+    e->prof.collect();
+    if (ms) *ms = e->prof.ms[cat];
+    if (launches) *launches = e->prof.n[cat];
+    if (work) *work = e->prof.work[cat];
+    UMAB_CATCH
+}
+
+const char* umab_profile_name(int32_t cat) { return (cat >= 0 && cat < P_COUNT) ? kProfNames[cat] : nullptr; }
+
 int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_bytes) {
     UMAB_TRY
     (void)e;
-    if (kernel_launches) *kernel_launches = g_launch_count;
+    if (kernel_launches) *kernel_launches = g_launch_count.load();
     if (device_bytes) *device_bytes = DevBuf::total;
     UMAB_CATCH
 }

@@ -20,13 +20,14 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 _lib = None
 
 ABI_VERSION = 1
+DEFAULT_GEMM = "simt"      # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs
 
 # every symbol include/umab.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "umab_abi_version", "umab_last_error", "umab_create", "umab_destroy", "umab_set_weight",
     "umab_finalize_weights", "umab_set_system", "umab_build_graph", "umab_graph_counts",
     "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_gemm",
-    "umab_debug_tensor", "umab_stats",
+    "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
 )
 
 
@@ -74,9 +75,14 @@ def load_library(path: Optional[str] = None):
     lib.umab_gemm.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.umab_debug_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.umab_profile.argtypes = [vp, i32]
+    lib.umab_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
+                                      ctypes.POINTER(ctypes.c_double)]
+    lib.umab_profile_name.argtypes = [i32]
+    lib.umab_profile_name.restype = ctypes.c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("umab_last_error", "umab_destroy", "umab_abi_version"):
+        if name not in ("umab_last_error", "umab_destroy", "umab_abi_version", "umab_profile_name"):
             fn.restype = i32
     if lib.umab_abi_version() != ABI_VERSION:
         raise RuntimeError("libumab.so ABI version mismatch: rebuild the extension")
@@ -178,7 +184,7 @@ class UmabEngine:
         self.device = int(device)
         self.n_atoms = len(z)
         if gemm_mode is None:
-            gemm_mode = {"simt": 0, "tc": 1}[os.environ.get("UMAB_GEMM", "simt")]
+            gemm_mode = {"simt": 0, "tc": 1}[os.environ.get("UMAB_GEMM", DEFAULT_GEMM)]
         cfg = UmabConfig(arch.sphere_channels, arch.hidden_channels, arch.num_distance_basis, arch.num_layers,
                          int(max_neighbors if max_neighbors is not None else arch.max_neighbors), self.device,
                          int(bool(debug)), int(gemm_mode),
@@ -259,6 +265,22 @@ class UmabEngine:
         if n.value == 0:
             return torch.empty(0, dtype=torch.float32)
         return torch.as_tensor(_DevPtr(ptr.value, n.value), device=f"cuda:{self.device}").clone().cpu()
+
+    def profile(self, enable: bool):
+        """Enable/disable (and reset) per-kernel-family CUDA-event timing."""
+        _check(self.lib, self.lib.umab_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """{family: {"ms": device ms, "launches": n, "work": FLOPs (gemm) or bytes}}."""
+        out, cat = {}, 0
+        while True:
+            name = self.lib.umab_profile_name(cat)
+            if not name:
+                return out
+            ms, n, wk = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+            _check(self.lib, self.lib.umab_profile_read(self._h, cat, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(wk)))
+            out[name.decode()] = {"ms": ms.value, "launches": n.value, "work": wk.value}
+            cat += 1
 
     def stats(self):
         a, b = ctypes.c_int64(), ctypes.c_int64()

@@ -1,0 +1,84 @@
+"""Image / displacement sharding across GPUs.
+
+Units (images of a string, FD displacements) are independent evaluations of the same model,
+so the data path has NO collective: each rank evaluates a contiguous block of units with its
+own replica of the merged weights.  The only exchange is one ``all_gather`` of the packed
+result ``[E (fp64) | F (fp32)]`` per optimizer step, so that every rank (and the optimizer that
+lives on rank 0) sees the whole string -- the new meaning of the reference's ``workers`` option
+(``pdb2reaction/uma_pysis.py:52-63, 213-242``; there: Ray actors + graph parallelism over ONE
+structure).
+
+Two drivers use this module:
+* ``CudaBackend`` (calculator.py): one process, one host thread per GPU, no collective at all;
+* ``SpmdEvaluator``: one process per GPU under ``torchrun`` (bench.py ``--gpus N``), NCCL
+  all-gather over NVLink (gloo on CPU in the tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_units: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous block partition; the first ``n_units % world`` ranks get one extra unit."""
+    base, extra = divmod(int(n_units), int(world))
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def pack_results(e: torch.Tensor, f: torch.Tensor, cap: int, n_atoms: int) -> torch.Tensor:
+    """[b] fp64 energies + [b, n, 3] fp32 forces -> flat fp32 record padded to ``cap`` images:
+    [cap x 2 floats holding the fp64 bits | cap x n x 3]."""
+    b = e.shape[0]
+    n3 = 3 * int(n_atoms)          # fixed record size on every rank, also for an empty shard
+    rec = torch.zeros(cap * 2 + cap * n3, dtype=torch.float32, device=f.device)
+    rec[: 2 * b] = e.to(torch.float64).contiguous().view(torch.float32)
+    rec[2 * cap: 2 * cap + b * n3] = f.reshape(-1)
+    return rec
+
+
+def unpack_results(rec: torch.Tensor, b: int, cap: int, n_atoms: int):
+    e = rec[: 2 * b].contiguous().view(torch.float64)
+    f = rec[2 * cap: 2 * cap + b * n_atoms * 3].reshape(b, n_atoms, 3)
+    return e, f
+
+
+class SpmdEvaluator:
+    """Evaluate a full batch of images across the ranks of a process group.
+
+    ``evaluate_local(coords [b,N,3] float64 numpy) -> (E torch fp64 [b], F torch fp32 [b,N,3])``
+    on this rank's device.
+    """
+
+    def __init__(self, evaluate_local: Callable, n_atoms: int, group: Optional[dist.ProcessGroup] = None):
+        self.evaluate_local = evaluate_local
+        self.n_atoms = int(n_atoms)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def evaluate(self, coords_all: np.ndarray, gather: bool = True):
+        """coords_all [B,N,3] (identical on every rank) -> (E [B], F [B,N,3]) on every rank."""
+        b_tot = coords_all.shape[0]
+        bounds = shard_bounds(b_tot, self.world)
+        lo, hi = bounds[self.rank]
+        e, f = self.evaluate_local(coords_all[lo:hi])
+        if self.world == 1 or not gather:
+            return e, f
+        cap = max(h - l for l, h in bounds)
+        rec = pack_results(e, f, cap, self.n_atoms)
+        out = [torch.empty_like(rec) for _ in range(self.world)]
+        dist.all_gather(out, rec, group=self.group)          # the ONE collective per step
+        es, fs = [], []
+        for r, (l, h) in enumerate(bounds):
+            er, fr = unpack_results(out[r], h - l, cap, self.n_atoms)
+            es.append(er)
+            fs.append(fr)
+        return torch.cat(es), torch.cat(fs)

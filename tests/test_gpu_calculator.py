@@ -1,0 +1,72 @@
+"""-m gpu: the drop-in calculator on the real CUDA backend."""
+import numpy as np
+import pytest
+import torch
+
+from pdb2reaction_b200 import synth, uma_pysis, EV2AU, F_EVAA_2_AU, H_EVAA_2_AU
+from pdb2reaction_b200 import calculator as calc_mod
+from pdb2reaction_b200.shims import ANG2BOHR
+from conftest import merged_for
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def small_model(state4, arch4, monkeypatch):
+    """Route model='test-4x' to the 4-expert test weights (the default ID means 32 experts)."""
+    monkeypatch.setattr(calc_mod, "load_model_state", lambda model, arch: state4)
+    orig = calc_mod.CudaBackend.__init__
+
+    def init(self, elem, **kw):
+        kw["arch"] = arch4
+        orig(self, elem, **kw)
+
+    monkeypatch.setattr(calc_mod.CudaBackend, "__init__", init)
+    calc_mod._engine_cache.clear()
+    yield
+    calc_mod._engine_cache.clear()
+
+
+def test_get_forces_matches_oracle_in_atomic_units(built_lib, small_model, state4, arch4, hyper4):
+    from oracle import uma_ref
+    elem, imgs = synth.make_string(30, 3, 13)
+    z, merged = merged_for(state4, arch4, elem)
+    orc = uma_ref.OracleUMA(merged, z, dtype=torch.float32, hyper=hyper4)
+    e_ref, f_ref = orc.energy_forces(imgs)
+    calc = uma_pysis(model="test-4x", freeze_atoms=[2, 5])
+    r = calc.get_forces(elem, imgs[0] * ANG2BOHR)
+    assert abs(r["energy"] - e_ref[0].item() * EV2AU) < 1e-5 * 30 * EV2AU
+    ref = f_ref[0].double().numpy().copy()
+    ref[[2, 5]] = 0.0
+    assert np.abs(r["forces"] - ref.reshape(-1) * F_EVAA_2_AU).max() < 1e-4 * F_EVAA_2_AU
+    rb = calc.get_forces_batch(elem, imgs.reshape(3, -1) * ANG2BOHR)
+    assert np.abs(rb["energy"] - e_ref.double().numpy() * EV2AU).max() < 1e-5 * 30 * EV2AU
+    assert np.array_equal(rb["forces"][0], r["forces"])
+    e_only = calc.get_energy(elem, imgs[0] * ANG2BOHR)["energy"]
+    assert e_only == r["energy"]
+    # a second calculator of the same composition reuses the cached engine
+    n_eng = len(calc_mod._engine_cache)
+    uma_pysis(model="test-4x").get_energy(elem, imgs[0] * ANG2BOHR)
+    assert len(calc_mod._engine_cache) == n_eng
+
+
+def test_fd_hessian_against_oracle_analytic_hessian(built_lib, small_model, state4, arch4, hyper4):
+    from oracle import uma_ref
+    elem, coords = synth.make_cluster(10, 3)
+    z, merged = merged_for(state4, arch4, elem)
+    h_ref = uma_ref.OracleUMA(merged, z, dtype=torch.float64, hyper=hyper4).hessian(coords).reshape(30, 30).numpy()
+    h_ref = 0.5 * (h_ref + h_ref.T) * H_EVAA_2_AU
+    calc = uma_pysis(model="test-4x")
+    r = calc.get_hessian(elem, coords * ANG2BOHR)
+    h = r["hessian"]
+    assert h.is_cuda and h.dtype == torch.float64 and h.shape == (30, 30)
+    # fp32 forces differenced over 2e-3 A: ~1e-3 eV/A^2 noise on O(10) eV/A^2 entries
+    assert np.abs(h.cpu().numpy() - h_ref).max() < 5e-3 * H_EVAA_2_AU * max(1.0, np.abs(h_ref / H_EVAA_2_AU).max() / 10)
+    part = uma_pysis(model="test-4x", freeze_atoms=[0, 1, 2], return_partial_hessian=True, out_hess_torch=False,
+                     hessian_double=False).get_hessian(elem, coords * ANG2BOHR)["hessian"]
+    assert isinstance(part, np.ndarray) and part.shape == (21, 21) and part.dtype == np.float32
+
+
+def test_device_cpu_is_refused(built_lib):
+    with pytest.raises(RuntimeError, match="no CPU"):
+        uma_pysis(device="cpu").get_energy(["H", "H"], [0, 0, 0, 0, 0, 1.4])

@@ -1,0 +1,20 @@
+"""-m gpu: the library's GEMM kernels against a float64 torch matmul on the shapes the model uses."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1000, 128, 64), (4097, 1536, 128), (2500, 640, 768), (5000, 512, 512), (5000, 256, 256),
+          (2500, 384, 384), (5000, 512, 256), (5000, 256, 128), (2500, 768, 640), (3000, 128, 1536), (777, 64, 128)]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_simt_gemm(m, n, k, built_lib):
+    from pdb2reaction_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g)
+    c = engine.gemm(a, w, b, mode=0)
+    ref = (a.double() @ w.double().T + b.double())
+    assert (c.double() - ref).abs().max() < 2e-5 * ref.abs().max()

@@ -1,0 +1,158 @@
+"""Self-consistency of the CPU oracle (oracle/): the only pin available, since the reference
+ships no golden vectors and fairchem cannot be imported here (parity unpinned)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+from scipy.spatial import cKDTree
+from scipy.spatial.transform import Rotation
+
+from oracle import graph, uma_ref, wigner
+from pdb2reaction_b200 import synth, weights as W
+from pdb2reaction_b200.arch import UMAArch, atomic_numbers
+from conftest import merged_for
+
+
+def _ry(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _rx(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+
+def test_wigner_zjzjz_equals_representation_of_rotation():
+    rng = np.random.default_rng(0)
+    jd = [torch.from_numpy(j) for j in wigner.jd_matrices(2)]
+    for l in (0, 1, 2):
+        for _ in range(5):
+            a, b, c = rng.uniform(-3, 3, 3)
+            d = wigner.wigner_d(l, torch.tensor([a]), torch.tensor([b]), torch.tensor([c]), jd)[0].numpy()
+            ref = wigner.d_from_rotation(_ry(a) @ _rx(b) @ _ry(c), l)
+            assert np.abs(d - ref).max() < 1e-12
+            assert np.abs(d @ d.T - np.eye(2 * l + 1)).max() < 1e-12
+
+
+def test_wigner_is_a_homomorphism_and_rotates_edge_to_y():
+    rng = np.random.default_rng(1)
+    r1, r2 = Rotation.random(2, random_state=3).as_matrix()
+    for l in (1, 2):
+        assert np.abs(wigner.d_from_rotation(r1 @ r2, l)
+                      - wigner.d_from_rotation(r1, l) @ wigner.d_from_rotation(r2, l)).max() < 1e-12
+    v = torch.tensor(rng.normal(size=(7, 3)))
+    w = wigner.edge_wigner(v, 2)
+    n = (v / v.norm(dim=1, keepdim=True)).numpy()
+    assert np.abs(np.einsum("eab,eb->ea", w[:, 1:4, 1:4].numpy(), n) - np.array([0, 1, 0])).max() < 1e-12
+    # l=2 harmonics of n are mapped onto the m=0 component only
+    y2 = wigner.real_sh(n, 2)
+    out = np.einsum("eab,eb->ea", w[:, 4:9, 4:9].numpy(), y2)
+    assert np.abs(out - np.array([0, 0, 1.0, 0, 0])).max() < 1e-12
+
+
+def test_parameter_counts_match_published_uma_s():
+    """6.6 M active / ~150 M total, from shapes only (no 150 M allocation)."""
+    arch = UMAArch()
+    per_layer = sum(o * i for o, i in W.so2_shapes(arch).values())
+    assert per_layer == 1130496
+    small = W.init_uma_weights(UMAArch(num_experts=1), 0)
+    total1, active1 = W.count_params(small, UMAArch(num_experts=1))
+    assert total1 == active1
+    total32 = total1 + per_layer * 4 * 31 + 31 * 2 * arch.sphere_channels + 31   # + routing head rows
+    assert 6.2e6 < active1 < 6.7e6
+    assert 1.44e8 < total32 < 1.52e8
+
+
+@pytest.mark.parametrize("n,seed", [(20, 1), (300, 2)])
+def test_radius_graph_matches_kdtree(n, seed):
+    elem, coords = synth.make_cluster(n, seed)
+    pos = coords.astype(np.float32)
+    ei = graph.radius_graph(pos, [n], 6.0, 300)
+    tree = cKDTree(pos.astype(np.float64))
+    pairs = tree.query_pairs(6.0, output_type="ndarray")
+    assert ei.shape[1] == 2 * len(pairs)
+    assert np.all(np.diff(ei[1]) >= 0)                       # sorted by target
+    same = np.diff(ei[1]) == 0
+    assert np.all(np.diff(ei[0])[same] > 0)                  # then by source
+    # symmetric: (j -> i) present iff (i -> j)
+    fw = set(map(tuple, ei.T.tolist()))
+    assert all((t, s) in fw for s, t in fw)
+
+
+def test_radius_graph_cap_is_non_strict_and_images_do_not_mix():
+    elem, coords = synth.make_string(60, 2, 5)
+    pos = coords.reshape(-1, 3).astype(np.float32)
+    full = graph.radius_graph(pos, [60, 60], 6.0, 300)
+    assert np.all((full[0] < 60) == (full[1] < 60))
+    capped = graph.radius_graph(pos, [60, 60], 6.0, 8)
+    deg = np.bincount(capped[1], minlength=120)
+    assert deg.max() >= 9 and deg.max() < np.bincount(full[1], minlength=120).max()
+
+
+def test_invariances_and_forces(state4, arch4, hyper4):
+    elem, coords = synth.make_cluster(20, 1)
+    z, merged = merged_for(state4, arch4, elem)
+    orc = uma_ref.OracleUMA(merged, z, dtype=torch.float64, hyper=hyper4)
+    e, f = orc.energy_forces(coords)
+    assert 0.1 < f.pow(2).mean().sqrt() < 10.0               # O(1) eV/A so the 1e-4 tolerance bites
+    # un-merged MoLE == merged
+    orc_u = uma_ref.OracleUMA(state4, z, dtype=torch.float64, hyper=hyper4)
+    e_u, f_u = orc_u.energy_forces(coords)
+    assert (e - e_u).abs().max() < 1e-6 and (f - f_u).abs().max() < 1e-6
+    # rotation + translation
+    rot = Rotation.random(random_state=1).as_matrix()
+    e_r, f_r = orc.energy_forces(coords @ rot.T + 1.5)
+    assert abs((e_r - e).item()) < 2e-5
+    assert (f_r[0] - f[0] @ torch.tensor(rot.T)).abs().max() < 2e-5
+    # permutation of atoms
+    perm = np.random.default_rng(0).permutation(20)
+    orc_p = uma_ref.OracleUMA(merged, [z[i] for i in perm], dtype=torch.float64, hyper=hyper4)
+    e_p, f_p = orc_p.energy_forces(coords[perm])
+    assert abs((e_p - e).item()) < 1e-8 and (f_p[0] - f[0][perm]).abs().max() < 1e-8
+    # roll-angle (gamma) invariance
+    pos, zz, nat, ei = orc._prep(coords)
+    g = torch.rand(ei.shape[1], dtype=torch.float64, generator=torch.Generator().manual_seed(0)) * 6.28
+    e_g = uma_ref.energy(merged, pos, zz, nat, ei, hp=hyper4, gamma=g)
+    assert abs((e_g - e).item()) < 1e-9
+    # forces = -dE/dx by central differences in float64
+    for (a, c) in [(3, 1), (11, 0), (17, 2)]:
+        h = 1e-5
+        p1, p2 = pos.clone(), pos.clone()
+        p1[a, c] += h
+        p2[a, c] -= h
+        fd = -(uma_ref.energy(merged, p1, zz, nat, ei, hp=hyper4) - uma_ref.energy(merged, p2, zz, nat, ei, hp=hyper4)) / (2 * h)
+        assert abs(fd.item() - f[0, a, c].item()) < 1e-6
+    # fp32 vs fp64
+    e32, f32 = uma_ref.OracleUMA(merged, z, dtype=torch.float32, hyper=hyper4).energy_forces(coords)
+    assert abs((e32.double() - e).item()) / 20 < 1e-5 and (f32.double() - f).abs().max() < 1e-4
+
+
+def test_batch_of_images_equals_single_images(state4, arch4, hyper4):
+    elem, imgs = synth.make_string(24, 3, 7)
+    z, merged = merged_for(state4, arch4, elem)
+    orc = uma_ref.OracleUMA(merged, z, dtype=torch.float64, hyper=hyper4, edge_chunk=100)
+    e, f = orc.energy_forces(imgs)
+    for k in range(3):
+        e1, f1 = orc.energy_forces(imgs[k])
+        assert abs((e1 - e[k]).item()) < 1e-9 and (f1[0] - f[k]).abs().max() < 1e-9
+
+
+def test_hessian_is_symmetric_and_matches_fd_of_forces(state4, arch4, hyper4):
+    elem, coords = synth.make_cluster(8, 3)
+    z, merged = merged_for(state4, arch4, elem)
+    orc = uma_ref.OracleUMA(merged, z, dtype=torch.float64, hyper=hyper4)
+    h = orc.hessian(coords).reshape(24, 24)
+    assert (h - h.T).abs().max() < 1e-8
+    pos, zz, nat, ei = orc._prep(coords)
+    k = 7
+    step = 1e-5
+    p1, p2 = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    with torch.no_grad():
+        p1.view(-1)[k] += step
+        p2.view(-1)[k] -= step
+    g1, = torch.autograd.grad(uma_ref.energy(merged, p1, zz, nat, ei, hp=hyper4).sum(), p1)
+    g2, = torch.autograd.grad(uma_ref.energy(merged, p2, zz, nat, ei, hp=hyper4).sum(), p2)
+    col = (g1 - g2).reshape(-1) / (2 * step)
+    assert (col - h[:, k]).abs().max() < 1e-5

@@ -1,0 +1,72 @@
+"""Image sharding: partition arithmetic, record packing and the world_size-2 gloo path of
+SpmdEvaluator (the N>1 bench path; NCCL on the GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pdb2reaction_b200.sharding import SpmdEvaluator, pack_results, shard_bounds, unpack_results
+
+
+def test_shard_bounds_cover_everything_contiguously():
+    for n in (0, 1, 7, 12, 32, 33):
+        for w in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, w)
+            assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [h - l for l, h in b]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert shard_bounds(12, 8) == [(0, 2), (2, 4), (4, 6), (6, 8), (8, 9), (9, 10), (10, 11), (11, 12)]
+
+
+def test_pack_roundtrip_is_bit_exact_for_fp64_energies():
+    e = torch.tensor([-1234567.123456789, 3.5e-9, 0.1], dtype=torch.float64)
+    f = torch.randn(3, 5, 3)
+    rec = pack_results(e, f, cap=4, n_atoms=5)
+    assert rec.dtype == torch.float32 and rec.numel() == 4 * 2 + 4 * 15
+    e2, f2 = unpack_results(rec, 3, 4, 5)
+    assert torch.equal(e, e2) and torch.equal(f, f2)
+
+
+def _toy_local(coords):
+    c = torch.from_numpy(np.asarray(coords, dtype=np.float64))
+    e = (c ** 2).sum((1, 2)) + 1e6
+    f = (-2 * c).float()
+    return e, f
+
+
+def _worker(rank, world, port, n_img, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        coords = rng.normal(size=(n_img, 6, 3))
+        ev = SpmdEvaluator(_toy_local, 6)
+        e, f = ev.evaluate(coords)
+        e_ref, f_ref = _toy_local(coords)
+        ok = torch.equal(e, e_ref) and torch.equal(f, f_ref)
+        q.put((rank, bool(ok), tuple(e.shape), tuple(f.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_img", [4, 5, 1])
+def test_spmd_evaluator_gloo_world2(n_img):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_img, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, es, fs in res:
+        assert ok and es == (n_img,) and fs == (n_img, 6, 3)

@@ -24,6 +24,7 @@ namespace umab {
 
 std::atomic<long long> g_launch_count{0};
 void gemm_tc(const GemmArgs& a, cudaStream_t st);   // gemm_tc.cu
+void gemm_tc_ex(const GemmArgs& a, cudaStream_t st, bool cache_weights);
 bool gemm_tc_supported(const GemmArgs& a);
 
 namespace {
@@ -661,7 +662,7 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     g.M = (int)m; g.N = n; g.K = k;
     if (mode == 1) {
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
-        gemm_tc(g, (cudaStream_t)stream);
+        gemm_tc_ex(g, (cudaStream_t)stream, false);      // test entry: never cache by pointer
     } else {
         gemm_simt(g, (cudaStream_t)stream);
     }

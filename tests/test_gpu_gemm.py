@@ -18,3 +18,17 @@ def test_simt_gemm(m, n, k, built_lib):
     c = engine.gemm(a, w, b, mode=0)
     ref = (a.double() @ w.double().T + b.double())
     assert (c.double() - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("m,n,k", [s for s in SHAPES if s[2] % 64 == 0 and s[1] % 32 == 0])
+@pytest.mark.parametrize("accumulate_bias", [False, True])
+def test_tensor_core_bf16x3_gemm(m, n, k, accumulate_bias, built_lib):
+    """tcgen05 path: bf16 hi/lo split, 3 MMAs per product, fp32 accumulation in TMEM -> ~4e-6 relative."""
+    from pdb2reaction_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(m * 3 + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g) if accumulate_bias else None
+    c = engine.gemm(a, w, b, mode=1)
+    ref = a.double() @ w.double().T + (b.double() if b is not None else 0.0)
+    assert (c.double() - ref).abs().max() < 2e-5 * ref.abs().max()

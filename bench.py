@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--images", type=int, default=32)
     p.add_argument("--seed", type=int, default=4)
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    p.add_argument("--gemm", default=os.environ.get("UMAB_GEMM", "auto"), choices=["auto", "simt", "tc"])
+    p.add_argument("--gemm", default=os.environ.get("UMAB_GEMM", "auto"), choices=["auto", "simt", "tc"])   # auto = engine default
     p.add_argument("--experts", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-atoms", type=int, default=None)
@@ -199,11 +199,8 @@ def main():
     from pdb2reaction_b200.arch import UMAArch
     from pdb2reaction_b200.shims import ANG2BOHR
 
-    if args.gemm != "auto":
-        os.environ["UMAB_GEMM"] = args.gemm
-    elif "UMAB_GEMM" not in os.environ:
-        os.environ["UMAB_GEMM"] = engine_mod.DEFAULT_GEMM
-    gemm_name = os.environ["UMAB_GEMM"]
+    os.environ["UMAB_GEMM"] = args.gemm
+    gemm_name = args.gemm if args.gemm != "auto" else ("tc" if args.atoms >= 100 else "simt")
     elem, imgs, total_images = build_inputs(args, rank, world)
     n_local = imgs.shape[0]
     arch = UMAArch(num_experts=args.experts)

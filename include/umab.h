@@ -49,7 +49,7 @@ typedef struct umab_config {
     int32_t max_neighbors;      /* 300 */
     int32_t device;             /* CUDA ordinal */
     int32_t debug;              /* 1: keep named intermediates for umab_debug_tensor */
-    int32_t gemm_mode;          /* 0: fp32 SIMT, 1: tcgen05 bf16x3 tensor-core path */
+    int32_t gemm_mode;          /* 0: fp32 SIMT, 1: tcgen05 bf16x3, 2: auto (tensor cores for images >= 100 atoms) */
     float cutoff;               /* 6.0 Angstrom */
     float edge_degree_rescale;  /* 5.0 */
     int64_t workspace_bytes;    /* per-chunk edge workspace budget; 0 = default */
@@ -89,7 +89,8 @@ UMAB_API int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, 
                                 double* energy_host, float* forces_host, void* stream);
 
 /* Standalone GEMM  C[M,N] = A[M,K] . W[N,K]^T (+bias), device pointers, for kernel unit tests
- * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3. */
+ * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3, 2 same with the bf16
+ * weight planes cached by pointer (timing loops only). */
 UMAB_API int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const float* bias_dev, float* c_dev,
                   int64_t m, int32_t n, int32_t k, void* stream);
 

@@ -23,8 +23,11 @@
 namespace umab {
 
 std::atomic<long long> g_launch_count{0};
-void gemm_tc(const GemmArgs& a, cudaStream_t st);   // gemm_tc.cu
-void gemm_tc_ex(const GemmArgs& a, cudaStream_t st, bool cache_weights);
+struct TcPlaneCache;                                  // gemm_tc.cu
+TcPlaneCache* tc_cache_create();
+void tc_cache_destroy(TcPlaneCache* c);
+void tc_cache_clear(TcPlaneCache* c);
+void gemm_tc(const GemmArgs& a, cudaStream_t st, TcPlaneCache* cache);
 bool gemm_tc_supported(const GemmArgs& a);
 
 namespace {
@@ -149,6 +152,7 @@ struct umab_engine {
     DevBuf e_dev, f_dev;
     // debug
     std::map<std::string, std::pair<DevBuf, size_t>> dbg;
+    TcPlaneCache* tc_cache = tc_cache_create();       // bf16 planes of this engine's weights
     // profiling + pinned host staging
     Prof prof;
     void* hp_pos = nullptr; void* hp_f = nullptr; void* hp_e = nullptr; size_t hp_cap = 0, hp_ecap = 0;
@@ -221,9 +225,13 @@ struct umab_engine {
     }
 
     // ------------------------------------------------------------------ helpers
+    // gemm_mode 0: fp32 SIMT; 1: tcgen05 bf16x3; 2 (auto): tensor cores for images of >= 100 atoms.  The
+    // choice depends on the image size only, never on the batch, so an image evaluated alone and
+    // inside a batch goes through the same arithmetic.
+    bool use_tc() const { return cfg.gemm_mode == 1 || (cfg.gemm_mode == 2 && n_atoms >= 100); }
     void gemm(const GemmArgs& a, cudaStream_t st) {
         timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
-            if (cfg.gemm_mode == 1 && gemm_tc_supported(a)) gemm_tc(a, st);
+            if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
             else gemm_simt(a, st);
         });
     }
@@ -498,6 +506,7 @@ struct umab_engine {
     }
 
     ~umab_engine() {
+        tc_cache_destroy(tc_cache);
         for (auto& kv : weights) kv.second.buf.release();
         DevBuf* all[] = {&z1, &pos_own, &zt, &deg, &thr, &row_ptr, &src, &tgt, &odeg, &sptr, &cursor, &stmp, &sedge,
                          &vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
@@ -561,6 +570,7 @@ int32_t umab_set_weight(umab_engine* e, const char* name, const float* host, siz
     w.numel = numel;
     UMAB_CUDA(cudaMemcpy(w.buf.p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
     e->finalized = false;
+    tc_cache_clear(e->tc_cache);                 // bf16 planes are derived from the fp32 weights
     UMAB_CATCH
 }
 
@@ -660,9 +670,12 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     GemmArgs g;
     g.A = a_dev; g.lda = k; g.W = w_dev; g.ldw = k; g.Cmat = c_dev; g.ldc = n; g.bias = bias_dev;
     g.M = (int)m; g.N = n; g.K = k;
-    if (mode == 1) {
+    if (mode == 1 || mode == 2) {
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
-        gemm_tc_ex(g, (cudaStream_t)stream, false);      // test entry: never cache by pointer
+        // mode 1: weight planes rebuilt on every call (never cached by pointer);
+        // mode 2: planes cached by pointer for timing loops (the caller keeps W alive and unchanged)
+        static TcPlaneCache* bench_cache = tc_cache_create();
+        gemm_tc(g, (cudaStream_t)stream, mode == 2 ? bench_cache : nullptr);
     } else {
         gemm_simt(g, (cudaStream_t)stream);
     }

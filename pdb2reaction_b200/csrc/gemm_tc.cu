@@ -11,11 +11,12 @@
 // bf16 hi/lo tiles straight into the 128B-swizzled K-major shared-memory layout tcgen05 expects,
 // so no extra HBM pass exists.
 //
-// CTA = 128 x BN output tile, 192 threads:
-//   warps 0-3  load fp32 A rows (LDG.128), split, st.shared swizzled, fence.proxy.async, arrive;
-//              afterwards they are the epilogue: tcgen05.ld TMEM -> regs -> (+bias,+C) -> STG.128
-//   warp 4     TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
-//   warp 5     single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
+// CTA = 128 x BN output tile, 320 threads:
+//   warps 0-7  each thread owns half a tile row: load fp32 (LDG.128, two k blocks ahead), split,
+//              st.shared swizzled, fence.proxy.async, arrive; afterwards they are the epilogue:
+//              tcgen05.ld TMEM -> regs -> (+bias,+C) -> STG.128 (warp w reads TMEM lane quadrant w%4)
+//   warp 8     TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
+//   warp 9     single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
 // smem ring of S stages {A_hi, A_lo, W_hi, W_lo}, mbarriers full_a / full_b / empty, tmem_full.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -32,7 +33,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k block = one 128 B swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int PRODUCER_THREADS = 256;
 constexpr int A_TILE_BYTES = BM * 128; // one bf16 plane of the A tile
 
 struct TcParams {
@@ -157,12 +159,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const long long m0 = (long long)blockIdx.y * BM;
     const int nkb = p.K / BK;
 
-    if (warp == 5 && lane == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full_a(s), 128); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+    if (warp == 9 && lane == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_a(s), PRODUCER_THREADS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -171,51 +173,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles
-        const int r = threadIdx.x;                      // tile row 0..127
+        const int r = threadIdx.x & 127;                // tile row
+        const int h = threadIdx.x >> 7;                 // which half (32 floats) of the 64-wide k block
         const long long m = m0 + r;
         const bool valid = m < p.M;
-        const float* arow = p.A + (valid ? m : 0) * p.lda;
+        const float* arow = p.A + (valid ? m : 0) * p.lda + h * 32;
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        // software pipeline: the loads of k block kb+1 are in flight while kb is split and stored
-        float4 v[16], nx[16];
+        // software pipeline: the loads of k blocks kb+1 and kb+2 are in flight while kb is split
+        float4 v[8], n1[8], n2[8];
         auto load_block = [&](int kb, float4* dst) {
-            if (valid) {
+            if (valid && kb < nkb) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(arow + kb * BK) + i);
+                for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(arow + kb * BK) + i);
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) dst[i] = f4zero();
+                for (int i = 0; i < 8; ++i) dst[i] = f4zero();
             }
         };
         load_block(0, v);
+        load_block(1, n1);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % S;
             const uint32_t ph = (uint32_t)(kb / S) & 1u;
-            if (kb + 1 < nkb) load_block(kb + 1, nx);
+            load_block(kb + 2, n2);
             mbar_wait(empty(s), ph ^ 1u);
             const uint32_t dh = a_hi(s) + row_off, dl = a_lo(s) + row_off;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint4 hi, lo;
                 split8(v[2 * c], v[2 * c + 1], hi, lo);
-                const uint32_t off = (((uint32_t)c) ^ sw) << 4;
+                const uint32_t off = (((uint32_t)(4 * h + c)) ^ sw) << 4;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dh + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dl + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_a(s));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = nx[i];
+            for (int i = 0; i < 8; ++i) { v[i] = n1[i]; n1[i] = n2[i]; }
         }
         // ===================== epilogue: TMEM -> registers -> global
         mbar_wait(tmem_full, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         float* crow = p.Cm + (valid ? m : 0) * p.ldc + n0;
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = h; ch < BN / 32; ch += 2) {
             uint32_t rr[32];
             tmem_ld32(lane_base + (uint32_t)(ch * 32), rr);
             if (valid) {
@@ -230,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ===================== TMA producer of the weight planes
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
@@ -269,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
@@ -342,26 +346,39 @@ Planes build_planes(const float* W, int N, int K, cudaStream_t st) {
     return p;
 }
 
-std::mutex g_cache_mu;
-std::map<std::tuple<int, const float*, int, int>, Planes> g_cache;    // (device, W, N, K)
-
 }  // namespace
+
+// bf16 weight planes + tensor maps, owned by whoever owns the fp32 weights (an engine)
+struct TcPlaneCache {
+    std::mutex mu;
+    std::map<std::tuple<const float*, int, int>, Planes> planes;
+    ~TcPlaneCache() { clear(); }
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv : planes) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
+        planes.clear();
+    }
+};
+TcPlaneCache* tc_cache_create() { return new TcPlaneCache(); }
+void tc_cache_destroy(TcPlaneCache* c) { delete c; }
+void tc_cache_clear(TcPlaneCache* c) { if (c) c->clear(); }
 
 bool gemm_tc_supported(const GemmArgs& a) {
     return a.batch == 1 && a.M >= 256 && a.K % BK == 0 && a.K >= BK && a.N % 32 == 0 && pick_bn(a.N) >= 32 &&
            a.lda % 4 == 0 && a.ldc % 4 == 0 && a.ldw == a.K;
 }
 
-void gemm_tc_ex(const GemmArgs& a, cudaStream_t st, bool cache_weights) {
+// cache == nullptr: planes are built for this call only (unit-test entry)
+void gemm_tc(const GemmArgs& a, cudaStream_t st, TcPlaneCache* cache) {
     if (!gemm_tc_supported(a)) throw CudaError("gemm_tc: unsupported shape");
     int dev = 0;
     UMAB_CUDA(cudaGetDevice(&dev));
     Planes pl;
-    if (cache_weights) {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
-        auto key = std::make_tuple(dev, a.W, a.N, a.K);
-        auto it = g_cache.find(key);
-        if (it == g_cache.end()) it = g_cache.emplace(key, build_planes(a.W, a.N, a.K, st)).first;
+    if (cache) {
+        std::lock_guard<std::mutex> lk(cache->mu);
+        auto key = std::make_tuple(a.W, a.N, a.K);
+        auto it = cache->planes.find(key);
+        if (it == cache->planes.end()) it = cache->planes.emplace(key, build_planes(a.W, a.N, a.K, st)).first;
         pl = it->second;
     } else {
         pl = build_planes(a.W, a.N, a.K, st);
@@ -382,13 +399,12 @@ void gemm_tc_ex(const GemmArgs& a, cudaStream_t st, bool cache_weights) {
     dim3 grid((unsigned)(a.N / pl.bn), (unsigned)((a.M + BM - 1) / BM));
     gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(pl.tm_hi, pl.tm_lo, p);
     UMAB_LAUNCH_CHECK();
-    if (!cache_weights) {
+    if (!cache) {
         UMAB_CUDA(cudaStreamSynchronize(st));
         cudaFree(pl.hi);
         cudaFree(pl.lo);
     }
 }
 
-void gemm_tc(const GemmArgs& a, cudaStream_t st) { gemm_tc_ex(a, st, true); }
 
 }  // namespace umab

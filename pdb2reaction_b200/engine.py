@@ -20,7 +20,9 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 _lib = None
 
 ABI_VERSION = 1
-DEFAULT_GEMM = "simt"      # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs
+# "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
+DEFAULT_GEMM = "auto"
+GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
 
 # every symbol include/umab.h declares (checked by tests/test_abi.py)
 EXPORTS = (
@@ -184,7 +186,7 @@ class UmabEngine:
         self.device = int(device)
         self.n_atoms = len(z)
         if gemm_mode is None:
-            gemm_mode = {"simt": 0, "tc": 1}[os.environ.get("UMAB_GEMM", DEFAULT_GEMM)]
+            gemm_mode = GEMM_MODES[os.environ.get("UMAB_GEMM", DEFAULT_GEMM)]
         cfg = UmabConfig(arch.sphere_channels, arch.hidden_channels, arch.num_distance_basis, arch.num_layers,
                          int(max_neighbors if max_neighbors is not None else arch.max_neighbors), self.device,
                          int(bool(debug)), int(gemm_mode),

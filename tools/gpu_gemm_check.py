@@ -24,9 +24,15 @@ def main():
         print(f"M={m:6d} N={n:5d} K={k:5d}  rel err simt {out['simt']:.2e}  tc {out['tc']:.2e}", flush=True)
     # throughput at bench-like sizes (weights re-split each call in this test entry: time the kernel only via events
     # around a second call is not possible here, so this is an upper bound on time)
-    for (m, n, k) in [(1 << 20, 640, 768), (1 << 21, 512, 512), (1 << 20, 1536, 128), (1 << 21, 256, 128)]:
+    E = 1 << 20
+    shapes = [(E, 128, 64), (E, 128, 128), (E, 1536, 128), (E, 640, 768), (2 * E, 512, 512), (2 * E, 256, 256),
+              (E, 384, 384), (2 * E, 512, 256), (2 * E, 256, 128), (E, 768, 640), (2 * E, 256, 512), (2 * E, 128, 256),
+              (E, 128, 1536), (E, 64, 128)]
+    keep = []
+    for (m, n, k) in shapes:
         a = torch.randn(m, k, device="cuda"); w = torch.randn(n, k, device="cuda") / k ** 0.5
-        for mode, name in ((0, "simt"), (1, "tc")):
+        keep.append(w)
+        for mode, name in ((2, "tc"),):
             engine.gemm(a, w, None, mode=mode)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

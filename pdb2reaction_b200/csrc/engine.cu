@@ -111,6 +111,17 @@ struct Prof {
     void reset() { collect(); for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; work[i] = 0; n[i] = 0; } }
 };
 
+// switch to the engine's device for the duration of a C-ABI call and restore the caller's
+// current device afterwards (the host may be driving several engines / torch on other GPUs)
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        UMAB_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 constexpr size_t EDGE_WS_FLOATS = 2304 + 2176 + 1152 + 1920 + 1536 + 4 * 128;   // 9600 per edge
 
 }  // namespace
@@ -549,7 +560,7 @@ int32_t umab_create(const umab_config* cfg, umab_engine** out) {
         cudaGetLastError();
         throw CudaError("no CUDA device available: umab has no CPU fallback");
     }
-    UMAB_CUDA(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);
     cudaDeviceProp prop;
     UMAB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major < 10) throw CudaError("umab kernels are built for sm_100a (Blackwell) only");
@@ -559,12 +570,20 @@ int32_t umab_create(const umab_config* cfg, umab_engine** out) {
     UMAB_CATCH
 }
 
-void umab_destroy(umab_engine* e) { delete e; }
+void umab_destroy(umab_engine* e) {
+    if (!e) return;
+    try {
+        DeviceGuard guard(e->cfg.device);
+        delete e;
+    } catch (...) {
+        delete e;
+    }
+}
 
 int32_t umab_set_weight(umab_engine* e, const char* name, const float* host, size_t numel) {
     UMAB_TRY
     if (!e || !name || !host) throw CudaError("null argument");
-    UMAB_CUDA(cudaSetDevice(e->cfg.device));
+    DeviceGuard guard(e->cfg.device);
     Weight& w = e->weights[name];
     w.buf.ensure(std::max<size_t>(numel, 4) * sizeof(float));
     w.numel = numel;
@@ -586,7 +605,7 @@ int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms) 
     if (!e || !z_host || n_atoms <= 0) throw CudaError("bad argument");
     for (int i = 0; i < n_atoms; ++i)
         if (z_host[i] < 0 || z_host[i] >= 100) throw CudaError("atomic number outside the embedding table");
-    UMAB_CUDA(cudaSetDevice(e->cfg.device));
+    DeviceGuard guard(e->cfg.device);
     e->z1.ensure(sizeof(int) * n_atoms);
     UMAB_CUDA(cudaMemcpy(e->z1.p, z_host, sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
     e->n_atoms = n_atoms;
@@ -597,7 +616,7 @@ int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms) 
 int32_t umab_build_graph(umab_engine* e, const float* pos_dev, int32_t n_images, void* stream) {
     UMAB_TRY
     if (!e || !pos_dev) throw CudaError("null argument");
-    UMAB_CUDA(cudaSetDevice(e->cfg.device));
+    DeviceGuard guard(e->cfg.device);
     e->build_graph(pos_dev, n_images, (cudaStream_t)stream);
     UMAB_CATCH
 }
@@ -613,6 +632,7 @@ int32_t umab_graph_counts(umab_engine* e, int64_t* n_nodes, int64_t* n_edges) {
 int32_t umab_graph_copy(umab_engine* e, int32_t* src_dev, int32_t* tgt_dev, int32_t* row_ptr_dev, void* stream) {
     UMAB_TRY
     if (!e) throw CudaError("null argument");
+    DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     if (src_dev && e->n_edges) UMAB_CUDA(cudaMemcpyAsync(src_dev, e->src.p, sizeof(int) * e->n_edges, cudaMemcpyDeviceToDevice, st));
     if (tgt_dev && e->n_edges) UMAB_CUDA(cudaMemcpyAsync(tgt_dev, e->tgt.p, sizeof(int) * e->n_edges, cudaMemcpyDeviceToDevice, st));
@@ -624,7 +644,7 @@ int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_t n_image
                            float* forces_dev, void* stream) {
     UMAB_TRY
     if (!e || !pos_dev || !energy_dev) throw CudaError("null argument");
-    UMAB_CUDA(cudaSetDevice(e->cfg.device));
+    DeviceGuard guard(e->cfg.device);
     e->evaluate(pos_dev, n_images, energy_dev, forces_dev, (cudaStream_t)stream);
     UMAB_CATCH
 }
@@ -634,7 +654,7 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
     UMAB_TRY
     if (!e || !pos_host || !energy_host) throw CudaError("null argument");
     if (e->n_atoms <= 0) throw CudaError("umab_set_system has not been called");
-    UMAB_CUDA(cudaSetDevice(e->cfg.device));
+    DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     size_t nb = (size_t)n_images * e->n_atoms * 3 * sizeof(float);
     e->pos_own.ensure(nb);
@@ -695,6 +715,7 @@ int32_t umab_debug_tensor(umab_engine* e, const char* name, const float** ptr_de
 int32_t umab_profile(umab_engine* e, int32_t enable) {
     UMAB_TRY
     if (!e) throw CudaError("null argument");
+    DeviceGuard guard(e->cfg.device);
     e->prof.reset();
     e->prof.on = enable != 0;
     UMAB_CATCH
@@ -703,6 +724,7 @@ int32_t umab_profile(umab_engine* e, int32_t enable) {
 int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work) {
     UMAB_TRY
     if (!e || cat < 0 || cat >= P_COUNT) throw CudaError("bad argument");
+    DeviceGuard guard(e->cfg.device);
     e->prof.collect();
     if (ms) *ms = e->prof.ms[cat];
     if (launches) *launches = e->prof.n[cat];

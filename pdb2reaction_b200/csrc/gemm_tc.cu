@@ -11,13 +11,17 @@
 // bf16 hi/lo tiles straight into the 128B-swizzled K-major shared-memory layout tcgen05 expects,
 // so no extra HBM pass exists.
 //
-// CTA = 128 x BN output tile, 320 threads:
-//   warps 0-7  each thread owns half a tile row: load fp32 (LDG.128, two k blocks ahead), split,
-//              st.shared swizzled, fence.proxy.async, arrive; afterwards they are the epilogue:
-//              tcgen05.ld TMEM -> regs -> (+bias,+C) -> STG.128 (warp w reads TMEM lane quadrant w%4)
-//   warp 8     TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
-//   warp 9     single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
-// smem ring of S stages {A_hi, A_lo, W_hi, W_lo}, mbarriers full_a / full_b / empty, tmem_full.
+// Persistent kernel: one CTA per SM loops over 128 x BN output tiles (N fastest, so concurrent CTAs
+// share an A tile through L2); 448 threads:
+//   warps 0-7   A producers: each thread owns half a tile row: LDG.128 fp32 (one k block ahead, across
+//               tile boundaries), split, st.shared swizzled, fence.proxy.async, mbarrier arrive
+//   warp 8      TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
+//   warp 9      single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
+//   warps 10-13 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
+//               fully coalesced STG.128; overlaps the next tile's main loop through the
+//               double-buffered TMEM accumulator (2 x tmem_cols columns)
+// smem ring of S stages {A_hi, A_lo, W_hi, W_lo}; mbarriers full_a / full_b / empty per stage and
+// tmem_full / tmem_empty per accumulator buffer.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -33,8 +37,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k block = one 128 B swizzle row
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
 constexpr int PRODUCER_THREADS = 256;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;   // per-warp transpose buffers of the epilogue
 constexpr int A_TILE_BYTES = BM * 128; // one bf16 plane of the A tile
 
 struct TcParams {
@@ -141,7 +146,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int BN = p.BN;
     const uint32_t w_tile_bytes = (uint32_t)BN * 128u;
     const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * w_tile_bytes;
-    const uint32_t bar_base = base + (uint32_t)S * stage_bytes;          // 8 B each
+    const uint32_t epi_base = base + (uint32_t)S * stage_bytes;           // 4 warps x 32 x 33 floats
+    const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;                 // 8 B each
     auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
     auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };
     auto w_hi = [&](int s) { return a_hi(s) + 2u * A_TILE_BYTES; };
@@ -149,23 +155,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     auto full_a = [&](int s) { return bar_base + 8u * (uint32_t)s; };
     auto full_b = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
     auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * S + s); };
-    const uint32_t tmem_full = bar_base + 8u * (uint32_t)(3 * S);
-    const uint32_t tmem_slot = tmem_full + 8u;
-    // generic pointer to the tmem slot for reading it back
+    auto tmem_full = [&](int b) { return bar_base + 8u * (uint32_t)(3 * S + b); };
+    auto tmem_empty = [&](int b) { return bar_base + 8u * (uint32_t)(3 * S + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(3 * S + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const int n0 = blockIdx.x * BN;
-    const long long m0 = (long long)blockIdx.y * BM;
     const int nkb = p.K / BK;
+    const int ntn = p.N / BN;                                   // tiles along N (fastest)
+    const int num_tiles = ntn * ((p.M + BM - 1) / BM);
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 9 && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_a(s), PRODUCER_THREADS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -174,31 +181,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp < 8) {
-        // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles
+        // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles.
+        // One flat loop over (tile, k block) so the prefetch runs across tile boundaries.
         const int r = threadIdx.x & 127;                // tile row
         const int h = threadIdx.x >> 7;                 // which half (32 floats) of the 64-wide k block
-        const long long m = m0 + r;
-        const bool valid = m < p.M;
-        const float* arow = p.A + (valid ? m : 0) * p.lda + h * 32;
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        // software pipeline: the loads of k blocks kb+1 and kb+2 are in flight while kb is split
-        float4 v[8], n1[8], n2[8];
-        auto load_block = [&](int kb, float4* dst) {
-            if (valid && kb < nkb) {
+        const int total = my_tiles * nkb;
+        float4 v[8], nx[8];
+        auto load_iter = [&](int g, float4* dst) {
+            const int lt = g / nkb, kb = g - lt * nkb;
+            const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+            const long long m = (long long)(tile / ntn) * BM + r;
+            if (g < total && m < p.M) {
+                const float4* src = reinterpret_cast<const float4*>(p.A + m * p.lda + kb * BK + h * 32);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = __ldg(reinterpret_cast<const float4*>(arow + kb * BK) + i);
+                for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dst[i] = f4zero();
             }
         };
-        load_block(0, v);
-        load_block(1, n1);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % S;
-            const uint32_t ph = (uint32_t)(kb / S) & 1u;
-            load_block(kb + 2, n2);
+        load_iter(0, v);
+        for (int g = 0; g < total; ++g) {
+            const int s = g % S;
+            const uint32_t ph = (uint32_t)(g / S) & 1u;
+            load_iter(g + 1, nx);
             mbar_wait(empty(s), ph ^ 1u);
             const uint32_t dh = a_hi(s) + row_off, dl = a_lo(s) + row_off;
 #pragma unroll
@@ -212,69 +220,102 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_a(s));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i] = n1[i]; n1[i] = n2[i]; }
-        }
-        // ===================== epilogue: TMEM -> registers -> global
-        mbar_wait(tmem_full, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        float* crow = p.Cm + (valid ? m : 0) * p.ldc + n0;
-        for (int ch = h; ch < BN / 32; ch += 2) {
-            uint32_t rr[32];
-            tmem_ld32(lane_base + (uint32_t)(ch * 32), rr);
-            if (valid) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 o = make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                                           __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-                    if (p.bias) o = f4add(o, __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32) + q));
-                    float* dst = crow + ch * 32 + q * 4;
-                    if (p.accumulate) o = f4add(o, ld4(dst));
-                    st4(dst, o);
-                }
-            }
+            for (int i = 0; i < 8; ++i) v[i] = nx[i];
         }
     } else if (warp == 8) {
         // ===================== TMA producer of the weight planes
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(empty(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_b(s), 2u * w_tile_bytes);
-                tma_load_2d(w_hi(s), &tm_hi, full_b(s), kb * BK, n0);
-                tma_load_2d(w_lo(s), &tm_lo, full_b(s), kb * BK, n0);
+            int g = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+                const int n0 = (tile % ntn) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % S;
+                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_b(s), 2u * w_tile_bytes);
+                    tma_load_2d(w_hi(s), &tm_hi, full_b(s), kb * BK, n0);
+                    tma_load_2d(w_lo(s), &tm_lo, full_b(s), kb * BK, n0);
+                }
             }
         }
-    } else {
-        // ===================== MMA issuer
+    } else if (warp == 9) {
+        // ===================== MMA issuer (double-buffered TMEM accumulators)
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+            int g = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int ab = lt & 1;
+                mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t dah = make_smem_desc(a_hi(s)), dal = make_smem_desc(a_lo(s));
-                const uint64_t dwh = make_smem_desc(w_hi(s)), dwl = make_smem_desc(w_lo(s));
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % S;
+                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                    mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t dah = make_smem_desc(a_hi(s)), dal = make_smem_desc(a_lo(s));
+                    const uint64_t dwh = make_smem_desc(w_hi(s)), dwl = make_smem_desc(w_lo(s));
 #pragma unroll
-                for (int j = 0; j < BK / 16; ++j) {
-                    const uint64_t adv = (uint64_t)(j * 2);      // 32 B per k step, in 16 B units
-                    umma_bf16(tmem_base, dah + adv, dwh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base, dah + adv, dwl + adv, idesc, 1u);
-                    umma_bf16(tmem_base, dal + adv, dwh + adv, idesc, 1u);
+                    for (int j = 0; j < BK / 16; ++j) {
+                        const uint64_t adv = (uint64_t)(j * 2);      // 32 B per k step, in 16 B units
+                        umma_bf16(d_tmem, dah + adv, dwh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, dah + adv, dwl + adv, idesc, 1u);
+                        umma_bf16(d_tmem, dal + adv, dwh + adv, idesc, 1u);
+                    }
+                    umma_commit(empty(s));       // frees the stage when these MMAs have read it
                 }
-                umma_commit(empty(s));       // frees the stage when these MMAs have read it
+                umma_commit(tmem_full(ab));      // accumulator of this tile complete
             }
-            umma_commit(tmem_full);          // accumulator complete
+        }
+    } else {
+        // ===================== epilogue warps 10-13: TMEM -> regs -> smem transpose -> coalesced STG
+        const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const uint32_t stg = epi_base + (uint32_t)q * (32u * 33u * 4u);
+        float* stg_ptr = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)));
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
+            const int n0 = (tile % ntn) * BN;
+            const long long mrow0 = (long long)(tile / ntn) * BM + q * 32;
+            const int ab = lt & 1;
+            mbar_wait(tmem_full(ab), ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)(ab * p.tmem_cols) + ((uint32_t)(q * 32) << 16);
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t rr[32];
+                tmem_ld32(taddr + (uint32_t)(ch * 32), rr);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg_ptr[lane * 33 + j] = __uint_as_float(rr[j]);
+                __syncwarp();
+                float4 bv = f4zero();
+                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + c4));
+#pragma unroll
+                for (int itr = 0; itr < 8; ++itr) {
+                    const int row = itr * 4 + rsub;
+                    const long long m = mrow0 + row;
+                    const float* sp = stg_ptr + row * 33 + c4;
+                    float4 o = make_float4(sp[0] + bv.x, sp[1] + bv.y, sp[2] + bv.z, sp[3] + bv.w);
+                    if (m < p.M) {
+                        float* dst = p.Cm + m * p.ldc + n0 + ch * 32 + c4;
+                        if (p.accumulate) o = f4add(o, ld4(dst));
+                        st4(dst, o);
+                    }
+                }
+            }
+            // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld32)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 8) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
     }
 }
 
@@ -391,12 +432,16 @@ void gemm_tc(const GemmArgs& a, cudaStream_t st, TcPlaneCache* cache) {
     int cols = 32;
     while (cols < pl.bn) cols *= 2;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 8 * (3 * p.stages + 2) + 16;
+    const size_t smem = (size_t)p.stages * stage_bytes + EPI_STAGE_BYTES + 1024 /*alignment slack*/ +
+                        8 * (3 * p.stages + 5) + 16;
     static std::once_flag attr_once[16];
     std::call_once(attr_once[dev & 15], [] {
         UMAB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     });
-    dim3 grid((unsigned)(a.N / pl.bn), (unsigned)((a.M + BM - 1) / BM));
+    static int n_sm[16] = {0};
+    if (!n_sm[dev & 15]) UMAB_CUDA(cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (long long)(a.N / pl.bn) * ((a.M + BM - 1) / BM);
+    dim3 grid((unsigned)std::min<long long>(tiles, n_sm[dev & 15]));
     gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(pl.tm_hi, pl.tm_lo, p);
     UMAB_LAUNCH_CHECK();
     if (!cache) {

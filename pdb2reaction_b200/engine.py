@@ -214,9 +214,8 @@ class UmabEngine:
         except Exception:
             pass
 
-    @staticmethod
-    def _stream_ptr():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream_ptr(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ------------------------------------------------------------------ device-resident API
     def energy_forces(self, pos: torch.Tensor, forces: bool = True):
@@ -252,7 +251,7 @@ class UmabEngine:
         src = torch.empty(ne_.value, dtype=torch.int32, device=pos.device)
         tgt = torch.empty(ne_.value, dtype=torch.int32, device=pos.device)
         _check(self.lib, self.lib.umab_graph_copy(self._h, src.data_ptr(), tgt.data_ptr(), None, self._stream_ptr()))
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
         return torch.stack([src.long(), tgt.long()]).cpu()
 
     def graph_counts(self):

@@ -409,13 +409,14 @@ struct umab_engine {
     // ------------------------------------------------------------------ full evaluation
     void evaluate(const float* pos, int nimg, double* energy_dev, float* forces_dev, cudaStream_t st) {
         if (!finalized) throw CudaError("umab_finalize_weights has not been called");
-        build_graph(pos, nimg, st);
+        timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(pos, nimg, st); });
         const int L = cfg.num_layers;
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
         const bool want_f = forces_dev != nullptr;
         vec.ensure(ne * 12); dist.ensure(ne * 4); env.ensure(ne * 4); wig.ensure(ne * WIG * 4); gauss.ensure(ne * NB * 4);
-        launch_geometry_fwd(pos, src.i(), tgt.i(), (int)n_edges, cfg.cutoff, vec.f(), dist.f(), env.f(), wig.f(), gauss.f(), st);
+        timed(P_GEOMETRY, (double)n_edges * (24.0 + 4.0 * (5 + WIG + NB)), st, [&] {
+            launch_geometry_fwd(pos, src.i(), tgt.i(), (int)n_edges, cfg.cutoff, vec.f(), dist.f(), env.f(), wig.f(), gauss.f(), st); });
         xs.resize(L + 1); x1s.resize(L); y1s.resize(L); gps.resize(L);
         for (auto& b : xs) b.ensure(nf);
         for (auto& b : x1s) b.ensure(nf);

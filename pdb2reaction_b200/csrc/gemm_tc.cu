@@ -12,12 +12,12 @@
 // so no extra HBM pass exists.
 //
 // Persistent kernel: one CTA per SM loops over 128 x BN output tiles (N fastest, so concurrent CTAs
-// share an A tile through L2); 704 threads:
-//   warps 0-15  A producers: each thread owns a quarter of a tile row: LDG.128 fp32 (three k blocks
-//               ahead, across tile boundaries), split, st.shared swizzled, fence.proxy.async, arrive
-//   warp 16     TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
-//   warp 17     single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
-//   warps 18-21 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
+// share an A tile through L2); 448 threads:
+//   warps 0-7   A producers: each thread owns half a tile row: LDG.128 fp32 (one k block ahead, across
+//               tile boundaries), split, st.shared swizzled, fence.proxy.async, mbarrier arrive
+//   warp 8      TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
+//   warp 9      single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
+//   warps 10-13 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
 //               fully coalesced STG.128; overlaps the next tile's main loop through the
 //               double-buffered TMEM accumulator (2 x tmem_cols columns)
 // smem ring of S stages {A_hi, A_lo, W_hi, W_lo}; mbarriers full_a / full_b / empty per stage and
@@ -37,9 +37,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k block = one 128 B swizzle row
-constexpr int TC_THREADS = 704;          // 16 producer warps + TMA + MMA + 4 epilogue warps
-constexpr int PRODUCER_THREADS = 512;
-constexpr int PRODUCER_WARPS = PRODUCER_THREADS / 32;
+constexpr int TC_THREADS = 448;
+constexpr int PRODUCER_THREADS = 256;
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;   // per-warp transpose buffers of the epilogue
 constexpr int A_TILE_BYTES = BM * 128; // one bf16 plane of the A tile
 
@@ -167,12 +166,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int num_tiles = ntn * ((p.M + BM - 1) / BM);
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == PRODUCER_WARPS + 1 && lane == 0) {
+    if (warp == 9 && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_a(s), PRODUCER_THREADS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == PRODUCER_WARPS) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -181,52 +180,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < PRODUCER_WARPS) {
+    if (warp < 8) {
         // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles.
-        // Each thread owns a quarter of a tile row (16 floats of the 64-wide k block); one flat loop
-        // over (tile, k block) with the loads of the next THREE k blocks in flight (across tiles).
+        // One flat loop over (tile, k block) so the prefetch runs across tile boundaries.
         const int r = threadIdx.x & 127;                // tile row
-        const int qd = threadIdx.x >> 7;                // quarter of the k block
+        const int h = threadIdx.x >> 7;                 // which half (32 floats) of the 64-wide k block
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
         const int total = my_tiles * nkb;
-        float4 b0[4], b1[4], b2[4], b3[4];
+        float4 v[8], nx[8];
         auto load_iter = [&](int g, float4* dst) {
             const int lt = g / nkb, kb = g - lt * nkb;
             const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
             const long long m = (long long)(tile / ntn) * BM + r;
             if (g < total && m < p.M) {
-                const float4* src = reinterpret_cast<const float4*>(p.A + m * p.lda + kb * BK + qd * 16);
+                const float4* src = reinterpret_cast<const float4*>(p.A + m * p.lda + kb * BK + h * 32);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+                for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = f4zero();
+                for (int i = 0; i < 8; ++i) dst[i] = f4zero();
             }
         };
-        load_iter(0, b0);
-        load_iter(1, b1);
-        load_iter(2, b2);
+        load_iter(0, v);
         for (int g = 0; g < total; ++g) {
             const int s = g % S;
             const uint32_t ph = (uint32_t)(g / S) & 1u;
-            load_iter(g + 3, b3);
+            load_iter(g + 1, nx);
             mbar_wait(empty(s), ph ^ 1u);
             const uint32_t dh = a_hi(s) + row_off, dl = a_lo(s) + row_off;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 uint4 hi, lo;
-                split8(b0[2 * c], b0[2 * c + 1], hi, lo);
-                const uint32_t off = (((uint32_t)(2 * qd + c)) ^ sw) << 4;
+                split8(v[2 * c], v[2 * c + 1], hi, lo);
+                const uint32_t off = (((uint32_t)(4 * h + c)) ^ sw) << 4;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dh + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dl + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_a(s));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { b0[i] = b1[i]; b1[i] = b2[i]; b2[i] = b3[i]; }
+            for (int i = 0; i < 8; ++i) v[i] = nx[i];
         }
-    } else if (warp == PRODUCER_WARPS) {
+    } else if (warp == 8) {
         // ===================== TMA producer of the weight planes
         if (lane == 0) {
             int g = 0;
@@ -243,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == PRODUCER_WARPS + 1) {
+    } else if (warp == 9) {
         // ===================== MMA issuer (double-buffered TMEM accumulators)
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
@@ -275,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue warps (last four): TMEM -> regs -> smem transpose -> coalesced STG
+        // ===================== epilogue warps 10-13: TMEM -> regs -> smem transpose -> coalesced STG
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
         const uint32_t stg = epi_base + (uint32_t)q * (32u * 33u * 4u);
         float* stg_ptr = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)));
@@ -318,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == PRODUCER_WARPS) {
+    if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
     }
 }

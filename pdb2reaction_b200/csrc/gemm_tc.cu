@@ -13,8 +13,9 @@
 //
 // Persistent kernel: one CTA per SM loops over 128 x BN output tiles (N fastest, so concurrent CTAs
 // share an A tile through L2); 448 threads:
-//   warps 0-7   A producers: each thread owns half a tile row: LDG.128 fp32 (one k block ahead, across
-//               tile boundaries), split, st.shared swizzled, fence.proxy.async, mbarrier arrive
+//   warps 0-7   A producers: coalesced LDG.128 of the fp32 tile (2 rows x 256 B per warp instruction, one
+//               k block ahead, across tile boundaries), split, st.shared swizzled (8 B per plane),
+//               fence.proxy.async, mbarrier arrive
 //   warp 8      TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
 //   warp 9      single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
 //   warps 10-13 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
@@ -39,7 +40,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k block = one 128 B swizzle row
 constexpr int TC_THREADS = 448;
 constexpr int PRODUCER_THREADS = 256;
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;   // per-warp transpose buffers of the epilogue
+constexpr int EPI_PITCH = 36;                       // floats per staged row (16 B aligned, conflict-free)
+constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_PITCH * 4;   // per-warp transpose buffers of the epilogue
 constexpr int A_TILE_BYTES = BM * 128; // one bf16 plane of the A tile
 
 struct TcParams {
@@ -146,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int BN = p.BN;
     const uint32_t w_tile_bytes = (uint32_t)BN * 128u;
     const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * w_tile_bytes;
-    const uint32_t epi_base = base + (uint32_t)S * stage_bytes;           // 4 warps x 32 x 33 floats
+    const uint32_t epi_base = base + (uint32_t)S * stage_bytes;           // 4 warps x 32 rows x EPI_PITCH floats
     const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;                 // 8 B each
     auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
     auto a_lo = [&](int s) { return a_hi(s) + A_TILE_BYTES; };
@@ -182,24 +184,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
     if (warp < 8) {
         // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles.
+        // Coalesced mapping: a warp owns 16 tile rows; each LDG.128 instruction covers 2 full rows of
+        // the k block (16 lanes x 16 B = 256 B per row -> 4 cache lines per instruction), 8
+        // instructions per k block.  A lane converts its 4 floats and stores 8 B of the hi and of
+        // the lo plane (2 smem wavefronts per 256 B instruction = the minimum).
         // One flat loop over (tile, k block) so the prefetch runs across tile boundaries.
-        const int r = threadIdx.x & 127;                // tile row
-        const int h = threadIdx.x >> 7;                 // which half (32 floats) of the 64-wide k block
-        const uint32_t row_off = (uint32_t)r * 128u;
-        const uint32_t sw = (uint32_t)(r & 7);
+        const int l16 = lane & 15;
+        const int rbase = warp * 16 + (lane >> 4);      // + 2*i
         const int total = my_tiles * nkb;
         float4 v[8], nx[8];
         auto load_iter = [&](int g, float4* dst) {
             const int lt = g / nkb, kb = g - lt * nkb;
             const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
-            const long long m = (long long)(tile / ntn) * BM + r;
-            if (g < total && m < p.M) {
-                const float4* src = reinterpret_cast<const float4*>(p.A + m * p.lda + kb * BK + h * 32);
+            const long long mb = (long long)(tile / ntn) * BM;
+            const float* src = p.A + (long long)kb * BK + l16 * 4;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = __ldg(src + i);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = f4zero();
+            for (int i = 0; i < 8; ++i) {
+                const long long m = mb + rbase + 2 * i;
+                dst[i] = (g < total && m < p.M) ? __ldg(reinterpret_cast<const float4*>(src + m * p.lda)) : f4zero();
             }
         };
         load_iter(0, v);
@@ -208,14 +210,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const uint32_t ph = (uint32_t)(g / S) & 1u;
             load_iter(g + 1, nx);
             mbar_wait(empty(s), ph ^ 1u);
-            const uint32_t dh = a_hi(s) + row_off, dl = a_lo(s) + row_off;
+            const uint32_t ah = a_hi(s), al = a_lo(s);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 hi, lo;
-                split8(v[2 * c], v[2 * c + 1], hi, lo);
-                const uint32_t off = (((uint32_t)(4 * h + c)) ^ sw) << 4;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dh + off), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dl + off), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+            for (int i = 0; i < 8; ++i) {
+                const int row = rbase + 2 * i;
+                const float4 x = v[i];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
+                                    h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+                __nv_bfloat162 ha, hb;
+                ha.x = h0; ha.y = h1; hb.x = h2; hb.y = h3;
+                const uint32_t l0 = pack_bf16(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+                const uint32_t l1 = pack_bf16(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+                const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(l16 >> 1)) ^ (uint32_t)(row & 7)) << 4) +
+                                     (uint32_t)(l16 & 1) * 8u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ah + off), "r"(*reinterpret_cast<uint32_t*>(&ha)),
+                             "r"(*reinterpret_cast<uint32_t*>(&hb)) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(al + off), "r"(l0), "r"(l1) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_a(s));
@@ -273,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     } else {
         // ===================== epilogue warps 10-13: TMEM -> regs -> smem transpose -> coalesced STG
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
-        const uint32_t stg = epi_base + (uint32_t)q * (32u * 33u * 4u);
+        const uint32_t stg = epi_base + (uint32_t)q * (32u * EPI_PITCH * 4u);
         float* stg_ptr = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)));
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         for (int lt = 0; lt < my_tiles; ++lt) {
@@ -289,7 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 tmem_ld32(taddr + (uint32_t)(ch * 32), rr);
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg_ptr[lane * 33 + j] = __uint_as_float(rr[j]);
+                for (int j = 0; j < 8; ++j)
+                    st4(stg_ptr + lane * EPI_PITCH + 4 * j,
+                        make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                    __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])));
                 __syncwarp();
                 float4 bv = f4zero();
                 if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + c4));
@@ -297,8 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 for (int itr = 0; itr < 8; ++itr) {
                     const int row = itr * 4 + rsub;
                     const long long m = mrow0 + row;
-                    const float* sp = stg_ptr + row * 33 + c4;
-                    float4 o = make_float4(sp[0] + bv.x, sp[1] + bv.y, sp[2] + bv.z, sp[3] + bv.w);
+                    float4 o = f4add(ld4(stg_ptr + row * EPI_PITCH + c4), bv);
                     if (m < p.M) {
                         float* dst = p.Cm + m * p.ldc + n0 + ch * 32 + c4;
                         if (p.accumulate) o = f4add(o, ld4(dst));

@@ -167,7 +167,7 @@ def run_reference(args):
     val = atoms_per_s / args.atoms
     sample = (f"per step: energy+forces of a {n_s}-atom sub-cluster of one {args.atoms}-atom image (graph rebuilt, "
               f"fp32, batch of 1, activation checkpointing); value = atoms/s / {args.atoms}")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -176,11 +176,29 @@ def run_reference(args):
                    "n_atoms": args.atoms, "n_images": args.images, "weights": "random-init uma-s-1p1 architecture, seed 0"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """Print the ONE JSON line on the real stdout (library chatter, e.g. NCCL's version banner,
+    has been diverted to stderr)."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # anything a library prints to fd 1 from now on goes to stderr
     if args.impl == "reference":
         return run_reference(args)
 
@@ -341,7 +359,7 @@ def main():
                                    "kind": "port",
                                    "sample": f"energy+forces of a {n_s}-atom sub-cluster of one image, oracle fp32, "
                                              f"graph rebuilt, {dtc:.1f} s per evaluation; value = atoms/s / {args.atoms}"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -53,10 +53,13 @@ typedef struct umab_config {
     float cutoff;               /* 6.0 Angstrom */
     float edge_degree_rescale;  /* 5.0 */
     int64_t workspace_bytes;    /* per-chunk edge workspace budget; 0 = default */
+    int64_t store_bytes;        /* HBM budget for keeping the conv outputs of all layers for the backward
+                                   (16.4 KB per edge and layer) instead of recomputing them: 0 = auto
+                                   (55 % of the device memory), -1 = never (always recompute) */
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 1
+#define UMAB_ABI_VERSION 2
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);

@@ -57,7 +57,7 @@ CALC_KW: Dict[str, Any] = {
 }
 
 FD_STEP_ANG = 1.0e-3            # reference uma_pysis.py:600
-MAX_ATOMS_PER_CALL = 49152      # node-state memory bound of one engine call (~100 KB / atom)
+MAX_ATOMS_PER_CALL = 49152      # FD-Hessian batching unit (the engine sub-batches further if needed)
 
 
 # ======================================================================================
@@ -135,7 +135,6 @@ class CudaBackend:
         """coords [B,N,3] float64 A -> (E [B] float64 eV, F [B,N,3] float32 eV/A | None)."""
         pos = np.ascontiguousarray(coords_ang, dtype=np.float32)   # the model sees fp32 positions (Q3)
         b, n = pos.shape[0], pos.shape[1]
-        per_call = max(1, MAX_ATOMS_PER_CALL // n)
         e_out = np.empty(b, dtype=np.float64)
         f_out = np.empty((b, n, 3), dtype=np.float32) if forces else None
         from .sharding import shard_bounds
@@ -143,12 +142,11 @@ class CudaBackend:
 
         def run(rank):
             lo, hi = bounds[rank]
-            for s in range(lo, hi, per_call):
-                t = min(hi, s + per_call)
-                e, f = self.engines[rank].energy_forces_host(pos[s:t], forces)
-                e_out[s:t] = e
+            if hi > lo:
+                e, f = self.engines[rank].energy_forces_host(pos[lo:hi], forces)   # sub-batched by the engine
+                e_out[lo:hi] = e
                 if forces:
-                    f_out[s:t] = f
+                    f_out[lo:hi] = f
 
         if self._pool is None:
             run(0)

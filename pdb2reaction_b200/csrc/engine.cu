@@ -159,6 +159,10 @@ struct umab_engine {
     // edge workspace
     DevBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2;
     long long chunk_cap = 0;
+    // store mode: conv-1 / conv-2 outputs of every layer are kept for the backward instead of being
+    // recomputed (16.4 KB per edge and layer of HBM) when they fit `store_bytes`
+    std::vector<DevBuf> ystore, zstore;
+    bool store_mode = false;
     // host staging for umab_energy_forces_host
     DevBuf e_dev, f_dev;
     // debug
@@ -345,6 +349,18 @@ struct umab_engine {
     float* Z1() { return wZ.f() + chunk_cap * 384; }
     float* Z2() { return wZ.f() + chunk_cap * (384 + 1024); }
 
+    struct YZ { float *y0, *y1, *y2, *z0, *z1, *z2; };
+    YZ yz_for(int layer, const Chunk& c) {
+        if (store_mode && layer >= 0) {
+            float* yb = ystore[layer].f();
+            float* zb = zstore[layer].f();
+            const long long E = n_edges;
+            return {yb + c.e0 * 640, yb + E * 640 + c.e0 * 1024, yb + E * 1664 + c.e0 * 512,
+                    zb + c.e0 * 384, zb + E * 384 + c.e0 * 1024, zb + E * 1408 + c.e0 * 512};
+        }
+        return {Y0(), Y1(), Y2(), Z0(), Z1(), Z2()};
+    }
+
     void radial_fwd(const RadialW& r, const Chunk& c, cudaStream_t st) {
         const long long e0 = c.e0;
         mm(gauss.f() + e0 * NB, NB, r.w1g, 128, NB, wU1.f(), 128, c.n_e, nullptr, 0, st);
@@ -363,43 +379,47 @@ struct umab_engine {
     }
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)
     void edge_fwd_chunk(const LayerW& w, const float* n1, const Chunk& c, int layer, bool dbg_on, cudaStream_t st) {
+        const YZ b = yz_for(layer, c);
         radial_fwd(w.rad, c, st);
         timed(P_GATHER, c.n_e * 15512.0 + c.n_nodes * 4608.0, st, [&] {
             launch_gather_rotate_scale(n1, src.i(), tgt.i(), wig.f(), wRAD.f(), c.e0, c.n_e, A0(), A1(), A2(), st); });
-        mm(A0(), 768, w.c1m0, 640, 768, Y0(), 640, c.n_e, w.c1m0_b, 0, st);
-        mm(A1(), 512, w.c1m1, 512, 512, Y1(), 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(A2(), 256, w.c1m2, 256, 256, Y2(), 256, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_COMBINE, c.n_e * 13312.0, st, [&] { launch_combine_gate_fwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), st); });
-        mm(B0(), 384, w.c2m0, 384, 384, Z0(), 384, c.n_e, w.c2m0_b, 0, st);
-        mm(B1(), 256, w.c2m1, 512, 256, Z1(), 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(B2(), 128, w.c2m2, 256, 128, Z2(), 256, 2LL * c.n_e, nullptr, 0, st);
+        mm(A0(), 768, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, 0, st);
+        mm(A1(), 512, w.c1m1, 512, 512, b.y1, 512, 2LL * c.n_e, nullptr, 0, st);
+        mm(A2(), 256, w.c1m2, 256, 256, b.y2, 256, 2LL * c.n_e, nullptr, 0, st);
+        timed(P_COMBINE, c.n_e * 13312.0, st, [&] { launch_combine_gate_fwd(b.y0, b.y1, b.y2, c.n_e, B0(), B1(), B2(), st); });
+        mm(B0(), 384, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, 0, st);
+        mm(B1(), 256, w.c2m1, 512, 256, b.z1, 512, 2LL * c.n_e, nullptr, 0, st);
+        mm(B2(), 128, w.c2m2, 256, 128, b.z2, 256, 2LL * c.n_e, nullptr, 0, st);
         if (dbg_on && chunks.size() == 1) {
             std::string p = "l" + std::to_string(layer) + ".";
             save_dbg(p + "rad", wRAD.f(), (size_t)c.n_e * 1536, st);
             save_dbg(p + "a0", A0(), (size_t)c.n_e * 768, st);
             save_dbg(p + "a1", A1(), (size_t)c.n_e * 1024, st);
             save_dbg(p + "a2", A2(), (size_t)c.n_e * 512, st);
-            save_dbg(p + "y0", Y0(), (size_t)c.n_e * 640, st);
-            save_dbg(p + "y1", Y1(), (size_t)c.n_e * 1024, st);
-            save_dbg(p + "y2", Y2(), (size_t)c.n_e * 512, st);
-            save_dbg(p + "z0", Z0(), (size_t)c.n_e * 384, st);
-            save_dbg(p + "z1", Z1(), (size_t)c.n_e * 1024, st);
-            save_dbg(p + "z2", Z2(), (size_t)c.n_e * 512, st);
+            save_dbg(p + "y0", b.y0, (size_t)c.n_e * 640, st);
+            save_dbg(p + "y1", b.y1, (size_t)c.n_e * 1024, st);
+            save_dbg(p + "y2", b.y2, (size_t)c.n_e * 512, st);
+            save_dbg(p + "z0", b.z0, (size_t)c.n_e * 384, st);
+            save_dbg(p + "z1", b.z1, (size_t)c.n_e * 1024, st);
+            save_dbg(p + "z2", b.z2, (size_t)c.n_e * 512, st);
         }
     }
-    void edge_bwd_chunk(const LayerW& w, const float* n1, const Chunk& c, const float* g_out, float* g_n1, cudaStream_t st) {
-        edge_fwd_chunk(w, n1, c, -1, false, st);
+    void edge_bwd_chunk(const LayerW& w, const float* n1, const Chunk& c, int layer, const float* g_out, float* g_n1,
+                        cudaStream_t st) {
+        const YZ b = yz_for(layer, c);
+        if (store_mode) radial_fwd(w.rad, c, st);            // only the radial weights are recomputed
+        else edge_fwd_chunk(w, n1, c, layer, false, st);     // recompute everything up to Z
         timed(P_ROTBACK_BWD, c.n_e * (2 * 7680.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0, st, [&] {
-            launch_rotate_back_bwd(0, Z0(), Z1(), Z2(), tgt.i(), wig.f(), env.f(), 1.0f, c.e0, c.n_e, g_out,
-                                   Z0(), Z1(), Z2(), g_env.f(), g_wig.f(), st); });
-        mm(Z0(), 384, w.c2m0_t, 384, 384, B0(), 384, c.n_e, nullptr, 0, st);
-        mm(Z1(), 512, w.c2m1_t, 256, 512, B1(), 256, 2LL * c.n_e, nullptr, 0, st);
-        mm(Z2(), 256, w.c2m2_t, 128, 256, B2(), 128, 2LL * c.n_e, nullptr, 0, st);
+            launch_rotate_back_bwd(0, b.z0, b.z1, b.z2, tgt.i(), wig.f(), env.f(), 1.0f, c.e0, c.n_e, g_out,
+                                   b.z0, b.z1, b.z2, g_env.f(), g_wig.f(), st); });
+        mm(b.z0, 384, w.c2m0_t, 384, 384, B0(), 384, c.n_e, nullptr, 0, st);
+        mm(b.z1, 512, w.c2m1_t, 256, 512, B1(), 256, 2LL * c.n_e, nullptr, 0, st);
+        mm(b.z2, 256, w.c2m2_t, 128, 256, B2(), 128, 2LL * c.n_e, nullptr, 0, st);
         timed(P_COMBINE_BWD, c.n_e * (8704.0 * 2 + 4608.0), st, [&] {
-            launch_combine_gate_bwd(Y0(), Y1(), Y2(), c.n_e, B0(), B1(), B2(), Y0(), Y1(), Y2(), st); });
-        mm(Y0(), 640, w.c1m0_t, 768, 640, A0(), 768, c.n_e, nullptr, 0, st);
-        mm(Y1(), 512, w.c1m1_t, 512, 512, A1(), 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(Y2(), 256, w.c1m2_t, 256, 256, A2(), 256, 2LL * c.n_e, nullptr, 0, st);
+            launch_combine_gate_bwd(b.y0, b.y1, b.y2, c.n_e, B0(), B1(), B2(), b.y0, b.y1, b.y2, st); });
+        mm(b.y0, 640, w.c1m0_t, 768, 640, A0(), 768, c.n_e, nullptr, 0, st);
+        mm(b.y1, 512, w.c1m1_t, 512, 512, A1(), 512, 2LL * c.n_e, nullptr, 0, st);
+        mm(b.y2, 256, w.c1m2_t, 256, 256, A2(), 256, 2LL * c.n_e, nullptr, 0, st);
         timed(P_GATHER_BWD, c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0, st, [&] {
             launch_gather_rotate_bwd(n1, row_ptr.i(), src.i(), wig.f(), wRAD.f(), c.e0, c.node0, c.n_nodes, A0(), A1(), A2(),
                                      wRAD.f(), Gbuf.f(), g_n1, g_wig.f(), st); });
@@ -414,6 +434,21 @@ struct umab_engine {
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
         const bool want_f = forces_dev != nullptr;
+        {
+            const double need = (double)n_edges * 4096.0 * 4.0 * L;
+            double budget = (double)cfg.store_bytes;
+            if (cfg.store_bytes == 0) {
+                size_t fr = 0, tot = 0;
+                UMAB_CUDA(cudaMemGetInfo(&fr, &tot));
+                budget = 0.55 * (double)tot;
+            }
+            store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
+            if (store_mode) {
+                ystore.resize(L); zstore.resize(L);
+                for (auto& b : ystore) b.ensure(ne * 2176 * 4);
+                for (auto& b : zstore) b.ensure(ne * 1920 * 4);
+            }
+        }
         vec.ensure(ne * 12); dist.ensure(ne * 4); env.ensure(ne * 4); wig.ensure(ne * WIG * 4); gauss.ensure(ne * NB * 4);
         timed(P_GEOMETRY, (double)n_edges * (24.0 + 4.0 * (5 + WIG + NB)), st, [&] {
             launch_geometry_fwd(pos, src.i(), tgt.i(), (int)n_edges, cfg.cutoff, vec.f(), dist.f(), env.f(), wig.f(), gauss.f(), st); });
@@ -445,8 +480,9 @@ struct umab_engine {
             save_dbg("l" + std::to_string(l) + ".n1", nbuf.p, (size_t)n_nodes * 9 * C, st);
             for (const Chunk& c : chunks) {
                 edge_fwd_chunk(w, nbuf.f(), c, l, true, st);
+                const YZ b = yz_for(l, c);
                 timed(P_ROTBACK, c.n_e * 7828.0 + c.n_nodes * 9216.0, st, [&] {
-                    launch_rotate_back_reduce(0, Z0(), Z1(), Z2(), row_ptr.i(), wig.f(), env.f(), 1.0f, c.e0, c.node0,
+                    launch_rotate_back_reduce(0, b.z0, b.z1, b.z2, row_ptr.i(), wig.f(), env.f(), 1.0f, c.e0, c.node0,
                                               c.n_nodes, xs[l].f(), x1s[l].f(), st); });
             }
             save_dbg("l" + std::to_string(l) + ".x1", x1s[l].p, (size_t)n_nodes * 9 * C, st);
@@ -493,7 +529,7 @@ struct umab_engine {
             launch_rms_bwd(x1s[l].f(), w.n2w, gn.f(), gx.f(), n_nodes, gx1.f(), st);   // g_x1 = gx + norm2^T g_n2
             // Edgewise adjoint
             launch_rms_fwd(xs[l].f(), w.n1w, w.n1b, csd, n_nodes, nbuf.f(), st);       // recompute n1
-            for (const Chunk& c : chunks) edge_bwd_chunk(w, nbuf.f(), c, gx1.f(), gn.f(), st);
+            for (const Chunk& c : chunks) edge_bwd_chunk(w, nbuf.f(), c, l, gx1.f(), gn.f(), st);
             timed(P_SRC_REDUCE, n_edges * 4612.0 + n_nodes * 9216.0, st, [&] {
                 launch_source_reduce(Gbuf.f(), sptr.i(), sedge.i(), n_nodes, gn.f(), st); });
             save_dbg("l" + std::to_string(l) + ".g_n1", gn.p, (size_t)n_nodes * 9 * C, st);
@@ -525,7 +561,7 @@ struct umab_engine {
                          &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &node_e, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1,
                          &wU2, &wH2, &e_dev, &f_dev};
         for (DevBuf* b : all) b->release();
-        for (auto* v : {&xs, &x1s, &y1s, &gps}) for (auto& b : *v) b.release();
+        for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore}) for (auto& b : *v) b.release();
         for (auto& kv : dbg) kv.second.first.release();
         if (h_pinned) cudaFreeHost(h_pinned);
         if (hp_pos) cudaFreeHost(hp_pos);

@@ -19,7 +19,7 @@ from .arch import UMAArch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -46,6 +46,7 @@ class UmabConfig(ctypes.Structure):
         ("cutoff", ctypes.c_float),
         ("edge_degree_rescale", ctypes.c_float),
         ("workspace_bytes", ctypes.c_int64),
+        ("store_bytes", ctypes.c_int64),
     ]
 
 
@@ -173,12 +174,17 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+MAX_ATOMS_PER_CALL = 49152        # node-state memory bound of one library call (~100 KB per atom)
+STORE_BYTES_PER_EDGE = 4096 * 4 * 4   # conv outputs kept for the backward: 16.4 KB per edge and layer, 4 layers
+
+
 class UmabEngine:
     """One engine = one (weights, composition, charge, spin, task) on one GPU."""
 
     def __init__(self, merged_weights: Dict[str, torch.Tensor], z: Sequence[int], arch: UMAArch = UMAArch(), *,
                  device: int = 0, cutoff: Optional[float] = None, max_neighbors: Optional[int] = None,
-                 debug: bool = False, gemm_mode: Optional[int] = None, workspace_bytes: int = 0):
+                 debug: bool = False, gemm_mode: Optional[int] = None, workspace_bytes: int = 0,
+                 store_bytes: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("pdb2reaction_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
         self.lib = load_library()
@@ -191,7 +197,7 @@ class UmabEngine:
                          int(max_neighbors if max_neighbors is not None else arch.max_neighbors), self.device,
                          int(bool(debug)), int(gemm_mode),
                          float(cutoff if cutoff is not None else arch.cutoff), float(arch.edge_degree_rescale),
-                         int(workspace_bytes))
+                         int(workspace_bytes), int(store_bytes))
         self.cfg = cfg
         h = ctypes.c_void_p()
         _check(self.lib, self.lib.umab_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -202,6 +208,27 @@ class UmabEngine:
         _check(self.lib, self.lib.umab_finalize_weights(self._h))
         zz = np.ascontiguousarray(np.asarray(list(z), dtype=np.int32))
         _check(self.lib, self.lib.umab_set_system(self._h, zz.ctypes.data, int(zz.size)))
+        self._store_budget = (-1 if store_bytes < 0 else store_bytes if store_bytes > 0 else
+                              0.55 * torch.cuda.get_device_properties(self.device).total_memory)
+        self._edges_per_atom = 85.0          # refined from the measured graphs
+
+    def images_per_call(self, forces: bool = True) -> int:
+        """How many images one library call should take: bounded by the node state, and -- when
+        forces are wanted -- sized so the per-layer conv outputs fit the store budget, which lets
+        the backward skip the recomputation of the SO(2) convolutions."""
+        n = self.n_atoms
+        cap = max(1, MAX_ATOMS_PER_CALL // n)
+        if forces and self._store_budget > 0:
+            per_image = n * self._edges_per_atom * STORE_BYTES_PER_EDGE * self.arch.num_layers / 4
+            fit = int(self._store_budget // per_image)
+            if fit >= 1:
+                cap = min(cap, fit)
+        return cap
+
+    def _note_graph(self):
+        nn_, ne_ = self.graph_counts()
+        if nn_ > 0:
+            self._edges_per_atom = max(20.0, 1.03 * ne_ / nn_)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -219,14 +246,21 @@ class UmabEngine:
 
     # ------------------------------------------------------------------ device-resident API
     def energy_forces(self, pos: torch.Tensor, forces: bool = True):
-        """pos [B, N, 3] float32 CUDA tensor (Angstrom) -> (E [B] float64, F [B,N,3] float32 | None)."""
+        """pos [B, N, 3] float32 CUDA tensor (Angstrom) -> (E [B] float64, F [B,N,3] float32 | None).
+        Large batches are passed to the library in sub-batches (``images_per_call``)."""
         assert pos.is_cuda and pos.dtype == torch.float32 and pos.dim() == 3 and pos.shape[1] == self.n_atoms
         pos = pos.contiguous()
         b = pos.shape[0]
         e = torch.empty(b, dtype=torch.float64, device=pos.device)
         f = torch.empty_like(pos) if forces else None
-        _check(self.lib, self.lib.umab_energy_forces(self._h, pos.data_ptr(), b, e.data_ptr(),
-                                                     f.data_ptr() if forces else None, self._stream_ptr()))
+        step = self.images_per_call(forces)
+        for s in range(0, b, step):
+            t = min(b, s + step)
+            _check(self.lib, self.lib.umab_energy_forces(self._h, pos[s:t].data_ptr(), t - s, e[s:t].data_ptr(),
+                                                         f[s:t].data_ptr() if forces else None, self._stream_ptr()))
+            if s == 0:
+                self._note_graph()
+                step = self.images_per_call(forces)
         return e, f
 
     # ------------------------------------------------------------------ host-buffer API (e2e path)
@@ -237,8 +271,17 @@ class UmabEngine:
         b = pos.shape[0]
         e = np.empty(b, dtype=np.float64)
         f = np.empty_like(pos) if forces else None
-        _check(self.lib, self.lib.umab_energy_forces_host(self._h, pos.ctypes.data, b, e.ctypes.data,
-                                                          f.ctypes.data if forces else None, self._stream_ptr()))
+        step = self.images_per_call(forces)
+        s = 0
+        while s < b:
+            t = min(b, s + step)
+            _check(self.lib, self.lib.umab_energy_forces_host(self._h, pos[s:t].ctypes.data, t - s, e[s:t].ctypes.data,
+                                                              f[s:t].ctypes.data if forces else None,
+                                                              self._stream_ptr()))
+            if s == 0:
+                self._note_graph()
+                step = self.images_per_call(forces)
+            s = t
         return e, f
 
     def graph(self, pos: torch.Tensor):

@@ -36,14 +36,14 @@ def test_abi_version_and_config_struct_layout(built_lib):
     from pdb2reaction_b200 import engine
     lib = engine.load_library()
     assert lib.umab_abi_version() == engine.ABI_VERSION
-    assert ctypes.sizeof(engine.UmabConfig) == 8 * 4 + 2 * 4 + 8
+    assert ctypes.sizeof(engine.UmabConfig) == 8 * 4 + 2 * 4 + 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback(built_lib, state4, arch4):
     from pdb2reaction_b200 import engine
     lib = engine.load_library()
-    cfg = engine.UmabConfig(128, 128, 64, 4, 300, 0, 0, 0, 6.0, 5.0, 0)
+    cfg = engine.UmabConfig(128, 128, 64, 4, 300, 0, 0, 0, 6.0, 5.0, 0, 0)
     h = ctypes.c_void_p()
     assert lib.umab_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"no CPU fallback" in lib.umab_last_error()

@@ -71,6 +71,21 @@ def test_edge_chunking_does_not_change_the_result(built_lib, state4, arch4):
     assert np.array_equal(e1, e2) and np.array_equal(f1, f2)
 
 
+def test_store_mode_equals_recompute_mode(built_lib, state4, arch4):
+    """Keeping the conv outputs for the backward (store mode) or recomputing them must give the
+    same bits: the same kernels run on the same data in the same order."""
+    elem, imgs = synth.make_string(150, 3, 12)
+    eng_store, _, _ = _engine(state4, arch4, elem)                      # auto: fits -> store mode
+    eng_rec, _, _ = _engine(state4, arch4, elem, store_bytes=-1)       # never store
+    eng_rec_chunked, _, _ = _engine(state4, arch4, elem, store_bytes=-1, workspace_bytes=9600 * 4 * 4000)
+    eng_store_chunked, _, _ = _engine(state4, arch4, elem, workspace_bytes=9600 * 4 * 4000)
+    pos = imgs.astype(np.float32)
+    e0, f0 = eng_store.energy_forces_host(pos)
+    for eng in (eng_rec, eng_rec_chunked, eng_store_chunked):
+        e1, f1 = eng.energy_forces_host(pos)
+        assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
+
+
 def test_stagewise_intermediates_match_the_staged_twin(built_lib, state4, arch4, hyper4):
     from oracle import staged, uma_ref
     elem, imgs = synth.make_string(24, 2, 7)

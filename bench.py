@@ -268,7 +268,7 @@ def main():
     launches = eng.stats()["kernel_launches"] - launches0
     fam = eng.profile_read()
     eng.profile(False)
-    n_nodes, n_edges = eng.graph_counts()
+    n_edges = eng.last_call_edges
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,7 +304,9 @@ def main():
             roof = {"kernel": "gemm_tc (tcgen05 bf16x3)" if gemm_name == "tc" else "gemm_simt (fp32 FFMA)",
                     "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": pk["source"] + f", bf16 dense sustained / {passes:g} passes",
-                    "flops_per_launch": d["work"] / max(d["launches"], 1), "ms_per_launch": per_launch_ms,
+                    "flops_per_launch": d["work"] / max(d["launches"], 1),
+                    "algorithmic_bytes_per_launch": d["bytes"] / max(d["launches"], 1),
+                    "algorithmic_hbm_gbs": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "ms_per_launch": per_launch_ms,
                     "launches": d["launches"], "share_of_step": d["ms"] / (ms * 1.0)}
         else:
             ach = d["work"] / (d["ms"] * 1e-3) / 1e9
@@ -316,7 +318,10 @@ def main():
         roof["traffic"] = None
         if os.path.exists(tpath):
             try:
-                roof["traffic"] = json.load(open(tpath)).get(roof["kernel"].split(" ")[0])
+                tj = json.load(open(tpath)).get(roof["kernel"].split(" ")[0])
+                if tj:          # ncu --set full capture (profiles/): measured DRAM bytes per launch
+                    roof["traffic"] = tj["dram_bytes_per_launch"]
+                    roof["traffic_capture"] = tj
             except Exception:
                 pass
         fam_out = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,

@@ -59,7 +59,7 @@ typedef struct umab_config {
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 2
+#define UMAB_ABI_VERSION 3
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);
@@ -103,10 +103,11 @@ UMAB_API int32_t umab_debug_tensor(umab_engine* e, const char* name, const float
 
 /* Per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline):
  * enable (resets the counters) / disable; read the accumulated device milliseconds, launch count
- * and algorithmic work (FLOPs for "gemm", bytes otherwise) of family `cat`;
+ * algorithmic work (FLOPs for "gemm", bytes otherwise) and algorithmic HBM bytes of family `cat`;
  * umab_profile_name(cat) is NULL past the last family. */
 UMAB_API int32_t umab_profile(umab_engine* e, int32_t enable);
-UMAB_API int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work);
+UMAB_API int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work,
+                                   double* bytes);
 UMAB_API const char* umab_profile_name(int32_t cat);
 
 /* Counters since creation: kernel launches issued by this library and bytes allocated. */

@@ -90,10 +90,10 @@ const char* const kProfNames[P_COUNT] = {"gemm", "gather_rotate_scale", "gather_
                                          "source_reduce", "ln_silu", "node_ops", "graph", "geometry"};
 struct Prof {
     bool on = false;
-    struct Rec { int cat; cudaEvent_t a, b; double work; };
+    struct Rec { int cat; cudaEvent_t a, b; double work, bytes; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
-    double ms[P_COUNT] = {0}; double work[P_COUNT] = {0}; long long n[P_COUNT] = {0};
+    double ms[P_COUNT] = {0}; double work[P_COUNT] = {0}; double bytes[P_COUNT] = {0}; long long n[P_COUNT] = {0};
     cudaEvent_t get() {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; UMAB_CUDA(cudaEventCreate(&e)); return e;
@@ -103,12 +103,12 @@ struct Prof {
             UMAB_CUDA(cudaEventSynchronize(r.b));
             float t = 0.f;
             UMAB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
-            ms[r.cat] += t; work[r.cat] += r.work; n[r.cat] += 1;
+            ms[r.cat] += t; work[r.cat] += r.work; bytes[r.cat] += r.bytes; n[r.cat] += 1;
             pool.push_back(r.a); pool.push_back(r.b);
         }
         recs.clear();
     }
-    void reset() { collect(); for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; work[i] = 0; n[i] = 0; } }
+    void reset() { collect(); for (int i = 0; i < P_COUNT; ++i) { ms[i] = 0; work[i] = 0; bytes[i] = 0; n[i] = 0; } }
 };
 
 // switch to the engine's device for the duration of a C-ABI call and restore the caller's
@@ -172,9 +172,9 @@ struct umab_engine {
     Prof prof;
     void* hp_pos = nullptr; void* hp_f = nullptr; void* hp_e = nullptr; size_t hp_cap = 0, hp_ecap = 0;
 
-    template <class F> void timed(int cat, double work, cudaStream_t st, F&& f) {
+    template <class F> void timed(int cat, double work, cudaStream_t st, F&& f, double bytes = -1.0) {
         if (!prof.on) { f(); return; }
-        Prof::Rec r{cat, prof.get(), prof.get(), work};
+        Prof::Rec r{cat, prof.get(), prof.get(), work, bytes < 0 ? work : bytes};
         UMAB_CUDA(cudaEventRecord(r.a, st));
         f();
         UMAB_CUDA(cudaEventRecord(r.b, st));
@@ -248,7 +248,8 @@ struct umab_engine {
         timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
             if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
             else gemm_simt(a, st);
-        });
+        }, /* algorithmic bytes: A and C once (+C again when accumulating), W once */
+           4.0 * a.batch * ((double)a.M * a.K + (double)a.M * a.N * (a.accumulate ? 2 : 1)) + 4.0 * a.N * (double)a.K);
     }
     void mm(const float* A, long long lda, const float* Wt, int N, int K, float* Cm, long long ldc, long long M,
             const float* bias, int accumulate, cudaStream_t st) {
@@ -758,7 +759,7 @@ int32_t umab_profile(umab_engine* e, int32_t enable) {
     UMAB_CATCH
 }
 
-int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work) {
+int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work, double* bytes) {
     UMAB_TRY
     if (!e || cat < 0 || cat >= P_COUNT) throw CudaError("bad argument");
     DeviceGuard guard(e->cfg.device);
@@ -766,6 +767,7 @@ int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* laun
     if (ms) *ms = e->prof.ms[cat];
     if (launches) *launches = e->prof.n[cat];
     if (work) *work = e->prof.work[cat];
+    if (bytes) *bytes = e->prof.bytes[cat];
     UMAB_CATCH
 }
 

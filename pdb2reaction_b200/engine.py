@@ -19,7 +19,7 @@ from .arch import UMAArch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -80,7 +80,7 @@ def load_library(path: Optional[str] = None):
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.umab_profile.argtypes = [vp, i32]
     lib.umab_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
-                                      ctypes.POINTER(ctypes.c_double)]
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.umab_profile_name.argtypes = [i32]
     lib.umab_profile_name.restype = ctypes.c_char_p
     for name in EXPORTS:
@@ -211,6 +211,7 @@ class UmabEngine:
         self._store_budget = (-1 if store_bytes < 0 else store_bytes if store_bytes > 0 else
                               0.55 * torch.cuda.get_device_properties(self.device).total_memory)
         self._edges_per_atom = 85.0          # refined from the measured graphs
+        self.last_call_edges = 0             # edges summed over the sub-batches of the last public call
 
     def images_per_call(self, forces: bool = True) -> int:
         """How many images one library call should take: bounded by the node state, and -- when
@@ -254,13 +255,16 @@ class UmabEngine:
         e = torch.empty(b, dtype=torch.float64, device=pos.device)
         f = torch.empty_like(pos) if forces else None
         step = self.images_per_call(forces)
-        for s in range(0, b, step):
+        s, self.last_call_edges = 0, 0
+        while s < b:
             t = min(b, s + step)
             _check(self.lib, self.lib.umab_energy_forces(self._h, pos[s:t].data_ptr(), t - s, e[s:t].data_ptr(),
                                                          f[s:t].data_ptr() if forces else None, self._stream_ptr()))
+            self.last_call_edges += self.graph_counts()[1]
             if s == 0:
                 self._note_graph()
                 step = self.images_per_call(forces)
+            s = t
         return e, f
 
     # ------------------------------------------------------------------ host-buffer API (e2e path)
@@ -272,12 +276,13 @@ class UmabEngine:
         e = np.empty(b, dtype=np.float64)
         f = np.empty_like(pos) if forces else None
         step = self.images_per_call(forces)
-        s = 0
+        s, self.last_call_edges = 0, 0
         while s < b:
             t = min(b, s + step)
             _check(self.lib, self.lib.umab_energy_forces_host(self._h, pos[s:t].ctypes.data, t - s, e[s:t].ctypes.data,
                                                               f[s:t].ctypes.data if forces else None,
                                                               self._stream_ptr()))
+            self.last_call_edges += self.graph_counts()[1]
             if s == 0:
                 self._note_graph()
                 step = self.images_per_call(forces)
@@ -321,9 +326,10 @@ class UmabEngine:
             name = self.lib.umab_profile_name(cat)
             if not name:
                 return out
-            ms, n, wk = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
-            _check(self.lib, self.lib.umab_profile_read(self._h, cat, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(wk)))
-            out[name.decode()] = {"ms": ms.value, "launches": n.value, "work": wk.value}
+            ms, n, wk, by = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+            _check(self.lib, self.lib.umab_profile_read(self._h, cat, ctypes.byref(ms), ctypes.byref(n),
+                                                        ctypes.byref(wk), ctypes.byref(by)))
+            out[name.decode()] = {"ms": ms.value, "launches": n.value, "work": wk.value, "bytes": by.value}
             cat += 1
 
     def stats(self):

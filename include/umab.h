@@ -59,7 +59,7 @@ typedef struct umab_config {
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 3
+#define UMAB_ABI_VERSION 4
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);
@@ -90,6 +90,13 @@ UMAB_API int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_
 /* Same with HOST buffers (pinned or pageable): H2D, compute, D2H and a final sync inside. */
 UMAB_API int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n_images,
                                 double* energy_host, float* forces_host, void* stream);
+
+/* Analytic Hessian columns (replaces torch.autograd.functional.hessian, pdb2reaction/uma_pysis.py:402-409):
+ * every image carries a displacement direction tangent_dev [n_images, n_atoms, 3]; the forward and the
+ * hand-written backward run on dual numbers and return dforces_dev = d(forces)/d(eps) = -H.tangent
+ * (fp32, eV/A^2 for unit tangents in A).  energy_dev / forces_dev may be NULL.  Device pointers. */
+UMAB_API int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const float* tangent_dev, int32_t n_images,
+                                 double* energy_dev, float* forces_dev, float* dforces_dev, void* stream);
 
 /* Standalone GEMM  C[M,N] = A[M,K] . W[N,K]^T (+bias), device pointers, for kernel unit tests
  * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3, 2 same with the bf16

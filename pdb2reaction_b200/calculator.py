@@ -154,6 +154,40 @@ class CudaBackend:
             list(self._pool.map(run, range(len(self.engines))))
         return e_out, f_out
 
+    def hessian_columns(self, coord_ang: np.ndarray, dofs: Sequence[int]) -> np.ndarray:
+        """Analytic Hessian columns H[:, k] (eV/A^2, float32) for k in ``dofs``: one dual-number
+        (value + tangent) pass of the forward and the hand-written backward per column, columns
+        sharded over the engines.  -> [len(dofs), 3N]."""
+        pos32 = np.ascontiguousarray(coord_ang, dtype=np.float32)
+        n = pos32.shape[0]
+        dofs = [int(k) for k in dofs]
+        out = np.empty((len(dofs), 3 * n), dtype=np.float32)
+        from .sharding import shard_bounds
+        bounds = shard_bounds(len(dofs), len(self.engines))
+
+        def run(rank):
+            lo, hi = bounds[rank]
+            if hi <= lo:
+                return
+            eng = self.engines[rank]
+            dev = torch.device("cuda", eng.device)
+            with torch.cuda.device(dev):
+                per = max(1, eng.images_per_call(True) // 2)
+                p1 = torch.from_numpy(pos32).to(dev)
+                for s in range(lo, hi, per):
+                    ks = dofs[s:min(hi, s + per)]
+                    pos = p1.unsqueeze(0).expand(len(ks), n, 3).contiguous()
+                    tan = torch.zeros(len(ks), 3 * n, device=dev, dtype=torch.float32)
+                    tan[torch.arange(len(ks), device=dev), torch.as_tensor(ks, device=dev)] = 1.0
+                    _, df = eng.forces_jvp(pos, tan.view(len(ks), n, 3))
+                    out[s:s + len(ks)] = (-df).reshape(len(ks), -1).cpu().numpy()
+
+        if self._pool is None:
+            run(0)
+        else:
+            list(self._pool.map(run, range(len(self.engines))))
+        return out
+
 
 # ======================================================================================
 class UMAcore:
@@ -296,6 +330,26 @@ class uma_pysis(Calculator):
             hmat = hmat.view(n_atoms, 3, n_atoms, 3)
         return {"energy": res0["energy"], "forces": f0, "hessian": hmat}
 
+    # ---------- analytic Hessian: dual-number columns (reference :394-415, :569-592) ----
+    def _build_analytic_hessian(self, coord_ang: np.ndarray):
+        core = self._core
+        dev = core.device
+        n_atoms = coord_ang.shape[0]
+        dof = 3 * n_atoms
+        active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
+        res0 = core.compute(coord_ang, forces=True)
+        cols = core.backend.hessian_columns(coord_ang, active_dof)            # [n_active_dof, 3N] fp32
+        hmat = torch.zeros((dof, dof), device=dev, dtype=torch.float32)       # model dtype, as the reference
+        idx = torch.as_tensor(active_dof, device=dev, dtype=torch.long)
+        hmat[:, idx] = torch.from_numpy(cols).to(dev).T                       # frozen columns stay 0 (:589-591)
+        if self.return_partial_hessian:
+            hmat = hmat.index_select(0, idx).index_select(1, idx)
+            na = len(active_atoms)
+            hmat = hmat.view(na, 3, na, 3)
+        else:
+            hmat = hmat.view(n_atoms, 3, n_atoms, 3)
+        return {"energy": res0["energy"], "forces": res0["forces"], "hessian": hmat}
+
     # ---------- pysisyphus API ---------------------------------------------------------
     def get_energy(self, elem, coords):
         """reference :689-693 (energy only: the backward pass is skipped, Q1)."""
@@ -311,23 +365,29 @@ class uma_pysis(Calculator):
         return {"energy": self._au_energy(res["energy"]), "forces": self._au_forces(f_ev)}
 
     def get_hessian(self, elem, coords):
-        """reference :708-780.  ``hessian_calc_mode``: anything but "analytical"/"analytic" means
-        FiniteDifference (Q8).  The analytic mode is currently served by the same batched
-        central-difference columns (second-order accurate, h = 1e-3 A) with a one-time warning;
-        hand-written HVP kernels are the planned replacement."""
+        """reference :708-780.  ``hessian_calc_mode``: "analytical"/"analytic" (any case) -> analytic
+        columns from dual-number passes through the same kernels (one per active DOF, no finite
+        differences, fp32 as the reference's autograd Hessian); anything else -> FiniteDifference
+        (Q8).  Unlike the reference, ``workers > 1`` does NOT force FD: columns shard over the GPUs."""
         self._ensure_core(elem)
         coord_ang = self._coords_ang(coords)
         mode = (self.hessian_calc_mode or "FiniteDifference").strip().lower()
-        if mode in ("analytical", "analytic") and not self._warned_analytic:
-            warnings.warn("hessian_calc_mode='Analytical': the B200 backend evaluates Hessian columns by "
-                          "batched central differences of analytic forces", RuntimeWarning, stacklevel=2)
-            self._warned_analytic = True
+        analytic = mode in ("analytical", "analytic")
+        if analytic and not hasattr(self._core.backend, "hessian_columns"):
+            if not self._warned_analytic:
+                warnings.warn("hessian_calc_mode='Analytical': this backend has no analytic columns; using "
+                              "batched central differences", RuntimeWarning, stacklevel=2)
+                self._warned_analytic = True
+            analytic = False
         try:
-            res = self._build_fd_hessian(coord_ang)
+            res = self._build_analytic_hessian(coord_ang) if analytic else self._build_fd_hessian(coord_ang)
         except torch.cuda.OutOfMemoryError as e:
             raise RuntimeError(
-                "Hessian computation failed due to CUDA out-of-memory. Reduce the batch by lowering "
-                "pdb2reaction_b200.calculator.MAX_ATOMS_PER_CALL.") from e
+                "Analytical Hessian computation failed due to CUDA out-of-memory. "
+                "Your GPU memory appears to be limited. Please switch to the finite-"
+                "difference Hessian by specifying `--hessian-calc-mode FiniteDifference` "
+                "in the external CLI, or `hessian_calc_mode=\"FiniteDifference\"` in this calculator."
+            ) from e
         f_ev = self._zero_frozen_forces_ev(res["forces"])
         return {"energy": self._au_energy(res["energy"]), "forces": self._au_forces(f_ev),
                 "hessian": self._au_hessian(res["hessian"])}

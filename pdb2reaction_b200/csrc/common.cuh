@@ -77,57 +77,4 @@ struct GemmArgs {
 
 void gemm_simt(const GemmArgs& a, cudaStream_t st);
 
-// ---------------------------------------------------------------- kernel launchers (one per .cu)
-void launch_neighbor_count(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int* deg, float* thr, cudaStream_t st);
-void launch_neighbor_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, const float* thr,
-                          const int* row_ptr, int* src, int* tgt, cudaStream_t st);
-void launch_scan(const int* in, int* out, int n, cudaStream_t st);
-void launch_source_csr(const int* src, int n_edges, int n_nodes, int* odeg, int* sptr, int* cursor, int* tmp,
-                       int* sedge, cudaStream_t st);
-
-void launch_geometry_fwd(const float* pos, const int* src, const int* tgt, int n_edges, float cutoff, float* vec,
-                         float* dist, float* env, float* wig, float* gauss, cudaStream_t st);
-void launch_geometry_bwd(const float* vec, const float* dist, const float* wig, const float* gauss,
-                         const float* g_gauss, const float* g_env, const float* g_wig, int n_edges, float cutoff,
-                         float* g_vec, cudaStream_t st);
-void launch_force_reduce(const float* g_vec, const int* row_ptr, const int* sptr, const int* sedge, int n_nodes,
-                         float* forces, cudaStream_t st);
-
-void launch_ln_silu_fwd(float* u, float* h, const float* gamma, const float* beta, const float* bias,
-                        const float* t_src, const float* t_tgt, const int* z, const int* src, const int* tgt,
-                        int rows, cudaStream_t st);
-void launch_ln_silu_bwd(const float* u, float* g, const float* gamma, const float* beta, int rows, cudaStream_t st);
-
-void launch_gather_rotate_scale(const float* x, const int* src, const int* tgt, const float* wig, const float* rad,
-                                long long e0, int n_e, float* A0, float* A1, float* A2, cudaStream_t st);
-void launch_gather_rotate_bwd(const float* x, const int* row_ptr, const int* src, const float* wig, const float* rad,
-                              long long e0, int node0, int n_nodes, const float* gA0, const float* gA1,
-                              const float* gA2, float* g_rad, float* G, float* g_x, float* g_wig, cudaStream_t st);
-void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st);
-void launch_combine_gate_fwd(const float* Y0, const float* Y1, const float* Y2, int n_e, float* B0, float* B1,
-                             float* B2, cudaStream_t st);
-void launch_combine_gate_bwd(const float* Y0, const float* Y1, const float* Y2, int n_e, const float* gB0,
-                             const float* gB1, const float* gB2, float* gY0, float* gY1, float* gY2, cudaStream_t st);
-void launch_rotate_back_reduce(int mode, const float* Z0, const float* Z1, const float* Z2, const int* row_ptr,
-                               const float* wig, const float* env, float scale, long long e0, int node0,
-                               int n_nodes, const float* base, float* out, cudaStream_t st);
-void launch_rotate_back_bwd(int mode, const float* Z0, const float* Z1, const float* Z2, const int* tgt,
-                            const float* wig, const float* env, float scale, long long e0, int n_e,
-                            const float* g_out, float* gZ0, float* gZ1, float* gZ2, float* g_env, float* g_wig,
-                            cudaStream_t st);
-
-void launch_embed(const float* sphere_emb, const float* csd, const int* z, int n_nodes, float* x, cudaStream_t st);
-void launch_rms_fwd(const float* x, const float* w_aff, const float* b_aff, const float* add0, int n_nodes, float* y,
-                    cudaStream_t st);
-void launch_rms_bwd(const float* x, const float* w_aff, const float* g_y, const float* g_add, int n_nodes,
-                    float* g_x, cudaStream_t st);
-void launch_ffn_gate_fwd(const float* y1, const float* gp, int n_nodes, float* a, cudaStream_t st);
-void launch_ffn_gate_bwd(const float* y1, const float* gp, const float* g_a, int n_nodes, float* g_y1, float* g_gp,
-                         cudaStream_t st);
-void launch_eltwise(int mode, const float* a, const float* b, long long n, float* out, cudaStream_t st);
-void launch_head_final(const float* p2, const float* w4, const float* b4, int n_nodes, float* node_e, float* g_p2,
-                       cudaStream_t st);
-void launch_energy_reduce(const float* node_e, int n_img, int n_atoms, double* energy, cudaStream_t st);
-void launch_tile_int(const int* in, int n, int reps, int* out, cudaStream_t st);
-
 }  // namespace umab

@@ -1,0 +1,154 @@
+// Dual numbers (value + one tangent) for forward-over-reverse differentiation of the SAME kernels.
+//
+// Every elementwise / gather / reduce kernel of the pipeline is a template on the scalar type S:
+//   S = float : the energy + force path (identical arithmetic to a plain float kernel)
+//   S = D1    : value and directional derivative d/d(eps) along a position tangent; running the
+//               forward AND the hand-written backward on duals yields d(forces)/d(eps) = -H.v, i.e.
+//               one analytic Hessian column per image (reference: torch.autograd.functional.hessian,
+//               pdb2reaction/uma_pysis.py:402-409).
+// Dual tensors are stored as two separate fp32 arrays (value plane, tangent plane) so the GEMMs --
+// linear in their activation operand -- simply run once per plane with the same weights.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace umab {
+
+struct D1 { float v, d; };
+struct D4 { float4 v, d; };
+
+template <class S> struct VecOf;
+template <> struct VecOf<float> { using type = float4; };
+template <> struct VecOf<D1> { using type = D4; };
+
+// ------------------------------------------------------------------ scalar ops
+__device__ __forceinline__ float val(float a) { return a; }
+__device__ __forceinline__ float val(D1 a) { return a.v; }
+template <class S> __device__ __forceinline__ S cst(float c);
+template <> __device__ __forceinline__ float cst<float>(float c) { return c; }
+template <> __device__ __forceinline__ D1 cst<D1>(float c) { return D1{c, 0.f}; }
+
+__device__ __forceinline__ D1 operator+(D1 a, D1 b) { return {a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ D1 operator-(D1 a, D1 b) { return {a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ D1 operator-(D1 a) { return {-a.v, -a.d}; }
+__device__ __forceinline__ D1 operator*(D1 a, D1 b) { return {a.v * b.v, fmaf(a.v, b.d, a.d * b.v)}; }
+__device__ __forceinline__ D1 operator*(D1 a, float b) { return {a.v * b, a.d * b}; }
+__device__ __forceinline__ D1 operator*(float a, D1 b) { return {a * b.v, a * b.d}; }
+__device__ __forceinline__ D1 operator+(D1 a, float b) { return {a.v + b, a.d}; }
+__device__ __forceinline__ D1 operator+(float a, D1 b) { return {a + b.v, b.d}; }
+__device__ __forceinline__ D1 operator-(D1 a, float b) { return {a.v - b, a.d}; }
+__device__ __forceinline__ D1 operator-(float a, D1 b) { return {a - b.v, -b.d}; }
+__device__ __forceinline__ D1& operator+=(D1& a, D1 b) { a.v += b.v; a.d += b.d; return a; }
+__device__ __forceinline__ D1 operator/(D1 a, D1 b) {
+    float q = a.v / b.v;
+    return {q, (a.d - q * b.d) / b.v};
+}
+__device__ __forceinline__ D1 operator/(D1 a, float b) { return {a.v / b, a.d / b}; }
+__device__ __forceinline__ D1 operator/(float a, D1 b) {
+    float q = a / b.v;
+    return {q, -q * b.d / b.v};
+}
+
+__device__ __forceinline__ float s_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ D1 s_sqrt(D1 a) { float q = sqrtf(a.v); return {q, a.d / (2.0f * q)}; }
+__device__ __forceinline__ float s_rsqrt(float a) { return rsqrtf(a); }
+__device__ __forceinline__ D1 s_rsqrt(D1 a) { float r = rsqrtf(a.v); return {r, -0.5f * r * r * r * a.d}; }
+__device__ __forceinline__ float s_exp(float a) { return expf(a); }
+__device__ __forceinline__ D1 s_exp(D1 a) { float e = expf(a.v); return {e, e * a.d}; }
+__device__ __forceinline__ float s_sigmoid(float a) { return sigmoidf_(a); }
+__device__ __forceinline__ D1 s_sigmoid(D1 a) { float s = sigmoidf_(a.v); return {s, s * (1.f - s) * a.d}; }
+__device__ __forceinline__ float s_silu(float a) { return siluf_(a); }
+__device__ __forceinline__ D1 s_silu(D1 a) {
+    float s = sigmoidf_(a.v);
+    return {a.v * s, s * (1.f + a.v * (1.f - s)) * a.d};
+}
+__device__ __forceinline__ float s_dsilu(float a) { return dsiluf_(a); }
+__device__ __forceinline__ D1 s_dsilu(D1 a) {      // silu'(x) and silu''(x) = s(1-s)(2 + x(1-2s))
+    float s = sigmoidf_(a.v);
+    return {s * (1.f + a.v * (1.f - s)), s * (1.f - s) * (2.f + a.v * (1.f - 2.f * s)) * a.d};
+}
+__device__ __forceinline__ float s_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ D1 s_fma(D1 a, D1 b, D1 c) { return a * b + c; }
+
+__device__ __forceinline__ D1 warp_sum(D1 a) { return {warp_sum(a.v), warp_sum(a.d)}; }
+__device__ __forceinline__ float s_shfl(float a, int lane) { return __shfl_sync(0xffffffffu, a, lane); }
+__device__ __forceinline__ D1 s_shfl(D1 a, int lane) {
+    return {__shfl_sync(0xffffffffu, a.v, lane), __shfl_sync(0xffffffffu, a.d, lane)};
+}
+__device__ __forceinline__ float s_shfl_xor(float a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+__device__ __forceinline__ D1 s_shfl_xor(D1 a, int m) {
+    return {__shfl_xor_sync(0xffffffffu, a.v, m), __shfl_xor_sync(0xffffffffu, a.d, m)};
+}
+
+// ------------------------------------------------------------------ 4-vector ops
+template <class V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ float4 vzero<float4>() { return f4zero(); }
+template <> __device__ __forceinline__ D4 vzero<D4>() { return D4{f4zero(), f4zero()}; }
+
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) { return f4add(a, b); }
+__device__ __forceinline__ D4 vadd(D4 a, D4 b) { return {f4add(a.v, b.v), f4add(a.d, b.d)}; }
+__device__ __forceinline__ float4 vsub(float4 a, float4 b) { return f4sub(a, b); }
+__device__ __forceinline__ D4 vsub(D4 a, D4 b) { return {f4sub(a.v, b.v), f4sub(a.d, b.d)}; }
+__device__ __forceinline__ float4 vmul(float4 a, float4 b) { return f4mul(a, b); }
+__device__ __forceinline__ D4 vmul(D4 a, D4 b) { return {f4mul(a.v, b.v), f4add(f4mul(a.v, b.d), f4mul(a.d, b.v))}; }
+__device__ __forceinline__ float4 vscale(float4 a, float s) { return f4scale(a, s); }
+__device__ __forceinline__ D4 vscale(D4 a, D1 s) { return {f4scale(a.v, s.v), f4add(f4scale(a.d, s.v), f4scale(a.v, s.d))}; }
+__device__ __forceinline__ D4 vscale(D4 a, float s) { return {f4scale(a.v, s), f4scale(a.d, s)}; }
+__device__ __forceinline__ float4 vneg(float4 a) { return f4scale(a, -1.f); }
+__device__ __forceinline__ D4 vneg(D4 a) { return {f4scale(a.v, -1.f), f4scale(a.d, -1.f)}; }
+// acc += s * b
+__device__ __forceinline__ void vfma(float4& acc, float s, float4 b) { f4fma(acc, s, b); }
+__device__ __forceinline__ void vfma(D4& acc, D1 s, D4 b) {
+    f4fma(acc.v, s.v, b.v);
+    f4fma(acc.d, s.v, b.d);
+    f4fma(acc.d, s.d, b.v);
+}
+__device__ __forceinline__ float vdot(float4 a, float4 b) { return f4dot(a, b); }
+__device__ __forceinline__ D1 vdot(D4 a, D4 b) { return {f4dot(a.v, b.v), f4dot(a.v, b.d) + f4dot(a.d, b.v)}; }
+__device__ __forceinline__ float vhsum(float4 a) { return f4hsum(a); }
+__device__ __forceinline__ D1 vhsum(D4 a) { return {f4hsum(a.v), f4hsum(a.d)}; }
+// a - s (broadcast scalar)
+__device__ __forceinline__ float4 vsubs(float4 a, float s) { return make_float4(a.x - s, a.y - s, a.z - s, a.w - s); }
+__device__ __forceinline__ D4 vsubs(D4 a, D1 s) { return {vsubs(a.v, s.v), vsubs(a.d, s.d)}; }
+
+#define UMAB_MAP4(name, fn)                                                                     \
+    __device__ __forceinline__ float4 name(float4 a) { return make_float4(fn(a.x), fn(a.y), fn(a.z), fn(a.w)); } \
+    __device__ __forceinline__ D4 name(D4 a) {                                                  \
+        D1 x = fn(D1{a.v.x, a.d.x}), y = fn(D1{a.v.y, a.d.y}), z = fn(D1{a.v.z, a.d.z}), w = fn(D1{a.v.w, a.d.w}); \
+        return {make_float4(x.v, y.v, z.v, w.v), make_float4(x.d, y.d, z.d, w.d)};              \
+    }
+UMAB_MAP4(vsilu, s_silu)
+UMAB_MAP4(vsigmoid, s_sigmoid)
+UMAB_MAP4(vdsilu, s_dsilu)
+#undef UMAB_MAP4
+
+// ------------------------------------------------------------------ global pointers (value plane [+ tangent plane])
+template <class S> struct GP;
+template <> struct GP<float> {
+    float* p;
+    __host__ __device__ GP operator+(long long o) const { return GP{p + o}; }
+    __host__ __device__ explicit operator bool() const { return p != nullptr; }
+    __device__ __forceinline__ float4 ld4(long long i) const { return *reinterpret_cast<const float4*>(p + i); }
+    __device__ __forceinline__ void st4(long long i, float4 x) const { *reinterpret_cast<float4*>(p + i) = x; }
+    __device__ __forceinline__ float ld(long long i) const { return p[i]; }
+    __device__ __forceinline__ void st(long long i, float x) const { p[i] = x; }
+};
+template <> struct GP<D1> {
+    float* v;
+    float* d;
+    __host__ __device__ GP operator+(long long o) const { return GP{v + o, d + o}; }
+    __host__ __device__ explicit operator bool() const { return v != nullptr; }
+    __device__ __forceinline__ D4 ld4(long long i) const {
+        return D4{*reinterpret_cast<const float4*>(v + i), *reinterpret_cast<const float4*>(d + i)};
+    }
+    __device__ __forceinline__ void st4(long long i, D4 x) const {
+        *reinterpret_cast<float4*>(v + i) = x.v;
+        *reinterpret_cast<float4*>(d + i) = x.d;
+    }
+    __device__ __forceinline__ D1 ld(long long i) const { return D1{v[i], d[i]}; }
+    __device__ __forceinline__ void st(long long i, D1 x) const { v[i] = x.v; d[i] = x.d; }
+};
+inline GP<float> gpf(const float* p) { return GP<float>{const_cast<float*>(p)}; }
+
+}  // namespace umab

@@ -11,22 +11,29 @@
 // (pdb2reaction/uma_pysis.py:385).  All kernels: one warp per edge (or per target node for the
 // segmented reductions), one float4 = 4 of the 128 channels per lane, fully coalesced 512 B rows.
 // Twin: oracle/staged.py (same function names).
-#include "common.cuh"
+#include "dual.cuh"
 
 namespace umab {
 
 namespace {
 
-struct WigReg { float d1[3][3]; float d2[5][5]; };
+// every kernel is a template on the scalar type S: float (energy/forces) or D1 (value + tangent)
+template <class S> struct WigReg { S d1[3][3]; S d2[5][5]; };
 
-__device__ __forceinline__ WigReg load_wig(const float* __restrict__ wig, long long e) {
-    WigReg w;
-    const float4* p = reinterpret_cast<const float4*>(wig + e * WIG);
-    float t[36];
+template <class S>
+__device__ __forceinline__ WigReg<S> load_wig(GP<S> wig, long long e) {
+    using V = typename VecOf<S>::type;
+    WigReg<S> w;
+    S t[36];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        float4 v = __ldg(p + i);
-        t[i * 4 + 0] = v.x; t[i * 4 + 1] = v.y; t[i * 4 + 2] = v.z; t[i * 4 + 3] = v.w;
+        V v = wig.ld4(e * WIG + 4 * i);
+        if constexpr (std::is_same<S, float>::value) {
+            t[i * 4 + 0] = v.x; t[i * 4 + 1] = v.y; t[i * 4 + 2] = v.z; t[i * 4 + 3] = v.w;
+        } else {
+            t[i * 4 + 0] = D1{v.v.x, v.d.x}; t[i * 4 + 1] = D1{v.v.y, v.d.y};
+            t[i * 4 + 2] = D1{v.v.z, v.d.z}; t[i * 4 + 3] = D1{v.v.w, v.d.w};
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -40,38 +47,40 @@ __device__ __forceinline__ WigReg load_wig(const float* __restrict__ wig, long l
 }
 
 // y = D x  (l-primary rows, block diagonal)
-__device__ __forceinline__ void rot_fwd(const WigReg& w, const float4* x, float4* y) {
+template <class S, class V>
+__device__ __forceinline__ void rot_fwd(const WigReg<S>& w, const V* x, V* y) {
     y[0] = x[0];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float4 s = f4zero();
+        V s = vzero<V>();
 #pragma unroll
-        for (int b = 0; b < 3; ++b) f4fma(s, w.d1[a][b], x[1 + b]);
+        for (int b = 0; b < 3; ++b) vfma(s, w.d1[a][b], x[1 + b]);
         y[1 + a] = s;
     }
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-        float4 s = f4zero();
+        V s = vzero<V>();
 #pragma unroll
-        for (int b = 0; b < 5; ++b) f4fma(s, w.d2[a][b], x[4 + b]);
+        for (int b = 0; b < 5; ++b) vfma(s, w.d2[a][b], x[4 + b]);
         y[4 + a] = s;
     }
 }
 // y = D^T x
-__device__ __forceinline__ void rot_bwd(const WigReg& w, const float4* x, float4* y) {
+template <class S, class V>
+__device__ __forceinline__ void rot_bwd(const WigReg<S>& w, const V* x, V* y) {
     y[0] = x[0];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float4 s = f4zero();
+        V s = vzero<V>();
 #pragma unroll
-        for (int b = 0; b < 3; ++b) f4fma(s, w.d1[b][a], x[1 + b]);
+        for (int b = 0; b < 3; ++b) vfma(s, w.d1[b][a], x[1 + b]);
         y[1 + a] = s;
     }
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-        float4 s = f4zero();
+        V s = vzero<V>();
 #pragma unroll
-        for (int b = 0; b < 5; ++b) f4fma(s, w.d2[b][a], x[4 + b]);
+        for (int b = 0; b < 5; ++b) vfma(s, w.d2[b][a], x[4 + b]);
         y[4 + a] = s;
     }
 }
@@ -86,15 +95,16 @@ __device__ __forceinline__ constexpr int r_off(int k) {
 }
 
 // totals of r[t] over the warp land in lane t (31 shuffles instead of 160)
-__device__ __forceinline__ float warp_transpose_sum32(float (&r)[32], int lane) {
+template <class S>
+__device__ __forceinline__ S warp_transpose_sum32(S (&r)[32], int lane) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
         const bool upper = (lane & o) != 0;
 #pragma unroll
         for (int i = 0; i < o; ++i) {
-            float send = upper ? r[i] : r[i + o];
-            float keep = upper ? r[i + o] : r[i];
-            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            S send = upper ? r[i] : r[i + o];
+            S keep = upper ? r[i + o] : r[i];
+            r[i] = keep + s_shfl_xor(send, o);
         }
     }
     return r[0];
@@ -102,55 +112,58 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&r)[32], int lane) 
 
 // partial (this lane's 4 channels) outer products  acc[(b,a)] += sum_c zl[b][c] g[a][c]  restricted to
 // the l=1 and l=2 blocks; slot order = Wigner record order (D1 row-major, then D2 row-major)
-__device__ __forceinline__ void wig_outer_acc(float (&acc)[34], const float4* zl, const float4* g) {
+template <class S, class V>
+__device__ __forceinline__ void wig_outer_acc(S (&acc)[34], const V* zl, const V* g) {
 #pragma unroll
     for (int b = 0; b < 3; ++b)
 #pragma unroll
-        for (int a = 0; a < 3; ++a) acc[b * 3 + a] += f4dot(zl[1 + b], g[1 + a]);
+        for (int a = 0; a < 3; ++a) acc[b * 3 + a] = acc[b * 3 + a] + vdot(zl[1 + b], g[1 + a]);
 #pragma unroll
     for (int b = 0; b < 5; ++b)
 #pragma unroll
-        for (int a = 0; a < 5; ++a) acc[9 + b * 5 + a] += f4dot(zl[4 + b], g[4 + a]);
+        for (int a = 0; a < 5; ++a) acc[9 + b * 5 + a] = acc[9 + b * 5 + a] + vdot(zl[4 + b], g[4 + a]);
 }
 
 // warp-reduce the 34 partials and add them (times `scale`) into g_wig[e]
-__device__ __forceinline__ void wig_grad_commit(float (&acc)[34], float scale, float* g_wig, long long e, int lane) {
-    float r[32];
+template <class S>
+__device__ __forceinline__ void wig_grad_commit(S (&acc)[34], S scale, GP<S> g_wig, long long e, int lane) {
+    S r[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = acc[i];
-    float tot = warp_transpose_sum32(r, lane);
-    float t32 = warp_sum(acc[32]);
-    float t33 = warp_sum(acc[33]);
-    float* p = g_wig + e * WIG;
-    p[lane] += scale * tot;
-    if (lane == 0) p[32] += scale * t32;
-    if (lane == 1) p[33] += scale * t33;
+    S tot = warp_transpose_sum32(r, lane);
+    S t32 = warp_sum(acc[32]);
+    S t33 = warp_sum(acc[33]);
+    const long long o = e * WIG;
+    g_wig.st(o + lane, g_wig.ld(o + lane) + scale * tot);
+    if (lane == 0) g_wig.st(o + 32, g_wig.ld(o + 32) + scale * t32);
+    if (lane == 1) g_wig.st(o + 33, g_wig.ld(o + 33) + scale * t33);
 }
 
 // ------------------------------------------------------------------ gather + rotate + radial scale
+template <class S>
 __global__ void __launch_bounds__(256)
-gather_rotate_scale_kernel(const float* __restrict__ x, const int* __restrict__ src, const int* __restrict__ tgt,
-                           const float* __restrict__ wig, const float* __restrict__ rad, long long e0, int n_e,
-                           float* __restrict__ A0, float* __restrict__ A1, float* __restrict__ A2) {
+gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
+                           long long e0, int n_e, GP<S> A0, GP<S> A1, GP<S> A2) {
+    using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long e = e0 + el;
-    const WigReg w = load_wig(wig, e);
-    const float* rp = rad + (long long)el * RAD1 + lane * 4;
-    float* const bufs[3] = {A0 + (long long)el * 768, A1 + (long long)el * 1024, A2 + (long long)el * 512};
+    const WigReg<S> w = load_wig<S>(wig, e);
+    const long long rp = (long long)el * RAD1 + lane * 4;
+    const GP<S> bufs[3] = {A0 + (long long)el * 768, A1 + (long long)el * 1024, A2 + (long long)el * 512};
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int node = half == 0 ? src[e] : tgt[e];
-        const float* xp = x + (long long)node * (9 * C) + lane * 4;
-        float4 xr[9], yl[9];
+        const long long xp = (long long)node * (9 * C) + lane * 4;
+        V xr[9], yl[9];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) xr[r] = ld4(xp + r * C);
+        for (int r = 0; r < 9; ++r) xr[r] = x.ld4(xp + r * C);
         rot_fwd(w, xr, yl);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            float4 rv = ld4(rp + r_off(k) + half * C);
-            st4(bufs[a_buf(k)] + a_off(k) + half * C + lane * 4, f4mul(yl[to_m(k)], rv));
+            V rv = rad.ld4(rp + r_off(k) + half * C);
+            bufs[a_buf(k)].st4(a_off(k) + half * C + lane * 4, vmul(yl[to_m(k)], rv));
         }
     }
 }
@@ -158,74 +171,73 @@ gather_rotate_scale_kernel(const float* __restrict__ x, const int* __restrict__ 
 // adjoint: one warp per TARGET node of the chunk, looping over its CSR row.
 //   g_rad (may alias rad) [E,1536];  G[e] = dL/dx[src] contribution [9,128] (l-primary);
 //   g_x[i] = sum over the row of the target-half contributions;  g_wig[e] += ...
+template <class S>
 __global__ void __launch_bounds__(256)
-gather_rotate_bwd_kernel(const float* __restrict__ x, const int* __restrict__ row_ptr, const int* __restrict__ src,
-                         const float* __restrict__ wig, const float* rad, long long e0, int node0, int n_nodes,
-                         const float* __restrict__ gA0, const float* __restrict__ gA1, const float* __restrict__ gA2,
-                         float* g_rad, float* __restrict__ G, float* __restrict__ g_x, float* __restrict__ g_wig) {
+gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __restrict__ src, GP<S> wig, GP<S> rad,
+                         long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, GP<S> g_rad, GP<S> G,
+                         GP<S> g_x, GP<S> g_wig) {
+    using V = typename VecOf<S>::type;
     const int nl = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (nl >= n_nodes) return;
     const int i = node0 + nl;
-    float4 acc_i[9];
+    V acc_i[9];
 #pragma unroll
-    for (int r = 0; r < 9; ++r) acc_i[r] = f4zero();
-    const float* xi_p = x + (long long)i * (9 * C) + lane * 4;
+    for (int r = 0; r < 9; ++r) acc_i[r] = vzero<V>();
+    const long long xi_p = (long long)i * (9 * C) + lane * 4;
 
     for (long long e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
         const long long el = e - e0;
-        const WigReg w = load_wig(wig, e);
-        const float* rp = rad + el * RAD1 + lane * 4;
-        float* grp = g_rad + el * RAD1 + lane * 4;
-        const float* const gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
-        float wacc[34];
+        const WigReg<S> w = load_wig<S>(wig, e);
+        const long long rp = el * RAD1 + lane * 4;
+        const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
+        S wacc[34];
 #pragma unroll
-        for (int q = 0; q < 34; ++q) wacc[q] = 0.f;
+        for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const float* xp = half == 0 ? x + (long long)src[e] * (9 * C) + lane * 4 : xi_p;
-            float4 xr[9], yl[9], gml[9];
-            float4 g_rad_v[6];      // radial groups 0,1,2 (m=0 rows), 3,4 (m=1: l=1,2), 5 (m=2)
+            const long long xp = half == 0 ? (long long)src[e] * (9 * C) + lane * 4 : xi_p;
+            V xr[9], yl[9], gml[9];
+            V g_rad_v[6];      // radial groups 0,1,2 (m=0 rows), 3,4 (m=1: l=1,2), 5 (m=2)
 #pragma unroll
-            for (int r = 0; r < 9; ++r) xr[r] = ld4(xp + r * C);
+            for (int r = 0; r < 9; ++r) xr[r] = x.ld4(xp + r * C);
             rot_fwd(w, xr, yl);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) g_rad_v[q] = f4zero();
+            for (int q = 0; q < 6; ++q) g_rad_v[q] = vzero<V>();
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                float4 ga = ld4(gbufs[a_buf(k)] + a_off(k) + half * C + lane * 4);
-                float4 rv = ld4(rp + r_off(k) + half * C);
+                V ga = gbufs[a_buf(k)].ld4(a_off(k) + half * C + lane * 4);
+                V rv = rad.ld4(rp + r_off(k) + half * C);
                 const int grp_id = k < 3 ? k : (k == 3 || k == 5 ? 3 : (k == 4 || k == 6 ? 4 : 5));
-                g_rad_v[grp_id] = f4add(g_rad_v[grp_id], f4mul(ga, yl[to_m(k)]));
-                gml[to_m(k)] = f4mul(ga, rv);
+                g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(k)]));
+                gml[to_m(k)] = vmul(ga, rv);
             }
             // every read of this lane's rad[e] columns of this half is done: g_rad may alias rad
 #pragma unroll
-            for (int q = 0; q < 3; ++q) st4(grp + q * 256 + half * C, g_rad_v[q]);
-            st4(grp + 768 + half * C, g_rad_v[3]);
-            st4(grp + 1024 + half * C, g_rad_v[4]);
-            st4(grp + 1280 + half * C, g_rad_v[5]);
+            for (int q = 0; q < 3; ++q) g_rad.st4(rp + q * 256 + half * C, g_rad_v[q]);
+            g_rad.st4(rp + 768 + half * C, g_rad_v[3]);
+            g_rad.st4(rp + 1024 + half * C, g_rad_v[4]);
+            g_rad.st4(rp + 1280 + half * C, g_rad_v[5]);
             // dL/dD[a][b] += sum_c gml[a][c] x[b][c]
             wig_outer_acc(wacc, gml, xr);
-            float4 gx[9];
+            V gx[9];
             rot_bwd(w, gml, gx);
             if (half == 0) {
-                float* gp = G + e * (9 * C) + lane * 4;
+                const long long gp = e * (9 * C) + lane * 4;
 #pragma unroll
-                for (int r = 0; r < 9; ++r) st4(gp + r * C, gx[r]);
+                for (int r = 0; r < 9; ++r) G.st4(gp + r * C, gx[r]);
             } else {
 #pragma unroll
-                for (int r = 0; r < 9; ++r) acc_i[r] = f4add(acc_i[r], gx[r]);
+                for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
             }
         }
-        wig_grad_commit(wacc, 1.0f, g_wig, e, lane);
+        wig_grad_commit(wacc, cst<S>(1.0f), g_wig, e, lane);
     }
-    float* op = g_x + (long long)i * (9 * C) + lane * 4;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) st4(op + r * C, acc_i[r]);
+    for (int r = 0; r < 9; ++r) g_x.st4(xi_p + r * C, acc_i[r]);
 }
 
-// g_x[j] += sum over out-edges of j of G[e]
+// g_x[j] += sum over out-edges of j of G[e]      (linear: the Hessian path runs it once per plane)
 __global__ void __launch_bounds__(256)
 source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, const int* __restrict__ sedge,
                      int n_nodes, float* __restrict__ g_x) {
@@ -246,280 +258,284 @@ source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, 
 }
 
 // ------------------------------------------------------------------ combine + gate (between the convs)
+template <class S>
 __global__ void __launch_bounds__(256)
-combine_gate_fwd_kernel(const float* __restrict__ Y0, const float* __restrict__ Y1, const float* __restrict__ Y2,
-                        int n_e, float* __restrict__ B0, float* __restrict__ B1, float* __restrict__ B2) {
+combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B1, GP<S> B2) {
+    using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
-    const float* y0 = Y0 + (long long)el * 640 + lane * 4;
-    const float* y1 = Y1 + (long long)el * 1024 + lane * 4;
-    const float* y2 = Y2 + (long long)el * 512 + lane * 4;
-    float4 g[2];
+    const long long y0 = (long long)el * 640 + lane * 4;
+    const long long y1 = (long long)el * 1024 + lane * 4;
+    const long long y2 = (long long)el * 512 + lane * 4;
+    V g[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) g[l] = vsigmoid(Y0.ld4(y0 + l * 128));
+    const long long b0 = (long long)el * 384 + lane * 4;
+    B0.st4(b0, vsilu(Y0.ld4(y0 + 256)));
+    B0.st4(b0 + 128, vmul(Y0.ld4(y0 + 384), g[0]));
+    B0.st4(b0 + 256, vmul(Y0.ld4(y0 + 512), g[1]));
+    const long long b1 = (long long)el * 512 + lane * 4;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        float4 v = ld4(y0 + l * 128);
-        g[l] = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+        V o_r = vsub(Y1.ld4(y1 + l * 128), Y1.ld4(y1 + 512 + 256 + l * 128));
+        V o_i = vadd(Y1.ld4(y1 + 512 + l * 128), Y1.ld4(y1 + 256 + l * 128));
+        B1.st4(b1 + l * 128, vmul(o_r, g[l]));
+        B1.st4(b1 + 256 + l * 128, vmul(o_i, g[l]));
     }
-    float* b0 = B0 + (long long)el * 384 + lane * 4;
-    float4 t0 = ld4(y0 + 256);
-    st4(b0, make_float4(siluf_(t0.x), siluf_(t0.y), siluf_(t0.z), siluf_(t0.w)));
-    st4(b0 + 128, f4mul(ld4(y0 + 384), g[0]));
-    st4(b0 + 256, f4mul(ld4(y0 + 512), g[1]));
-    float* b1 = B1 + (long long)el * 512 + lane * 4;
-#pragma unroll
-    for (int l = 0; l < 2; ++l) {
-        float4 o_r = f4sub(ld4(y1 + l * 128), ld4(y1 + 512 + 256 + l * 128));
-        float4 o_i = f4add(ld4(y1 + 512 + l * 128), ld4(y1 + 256 + l * 128));
-        st4(b1 + l * 128, f4mul(o_r, g[l]));
-        st4(b1 + 256 + l * 128, f4mul(o_i, g[l]));
-    }
-    float* b2 = B2 + (long long)el * 256 + lane * 4;
-    float4 p_r = f4sub(ld4(y2), ld4(y2 + 256 + 128));
-    float4 p_i = f4add(ld4(y2 + 256), ld4(y2 + 128));
-    st4(b2, f4mul(p_r, g[1]));
-    st4(b2 + 128, f4mul(p_i, g[1]));
+    const long long b2 = (long long)el * 256 + lane * 4;
+    V p_r = vsub(Y2.ld4(y2), Y2.ld4(y2 + 256 + 128));
+    V p_i = vadd(Y2.ld4(y2 + 256), Y2.ld4(y2 + 128));
+    B2.st4(b2, vmul(p_r, g[1]));
+    B2.st4(b2 + 128, vmul(p_i, g[1]));
 }
 
-// gY* may alias Y*, (gB* are read-only)
+// gY* may alias Y* (gB* are read-only)
+template <class S>
 __global__ void __launch_bounds__(256)
-combine_gate_bwd_kernel(const float* Y0, const float* Y1, const float* Y2, int n_e,
-                        const float* __restrict__ gB0, const float* __restrict__ gB1, const float* __restrict__ gB2,
-                        float* gY0, float* gY1, float* gY2) {
+combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, GP<S> gY0, GP<S> gY1,
+                        GP<S> gY2) {
+    using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
-    const float* y0 = Y0 + (long long)el * 640 + lane * 4;
-    const float* y1 = Y1 + (long long)el * 1024 + lane * 4;
-    const float* y2 = Y2 + (long long)el * 512 + lane * 4;
-    const float* gb0 = gB0 + (long long)el * 384 + lane * 4;
-    const float* gb1 = gB1 + (long long)el * 512 + lane * 4;
-    const float* gb2 = gB2 + (long long)el * 256 + lane * 4;
-    float4 sg[2], g_gate[2];
+    const long long y0 = (long long)el * 640 + lane * 4;
+    const long long y1 = (long long)el * 1024 + lane * 4;
+    const long long y2 = (long long)el * 512 + lane * 4;
+    const long long gb0 = (long long)el * 384 + lane * 4;
+    const long long gb1 = (long long)el * 512 + lane * 4;
+    const long long gb2 = (long long)el * 256 + lane * 4;
+    V sg[2], g_gate[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) sg[l] = vsigmoid(Y0.ld4(y0 + l * 128));
+    V t0 = Y0.ld4(y0 + 256), t1 = Y0.ld4(y0 + 384), t2 = Y0.ld4(y0 + 512);
+    V gb00 = gB0.ld4(gb0), gb01 = gB0.ld4(gb0 + 128), gb02 = gB0.ld4(gb0 + 256);
+    g_gate[0] = vmul(gb01, t1);
+    g_gate[1] = vmul(gb02, t2);
+    V g_or[2], g_oi[2];
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        float4 v = ld4(y0 + l * 128);
-        sg[l] = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+        V o_r = vsub(Y1.ld4(y1 + l * 128), Y1.ld4(y1 + 512 + 256 + l * 128));
+        V o_i = vadd(Y1.ld4(y1 + 512 + l * 128), Y1.ld4(y1 + 256 + l * 128));
+        V br = gB1.ld4(gb1 + l * 128), bi = gB1.ld4(gb1 + 256 + l * 128);
+        g_gate[l] = vadd(g_gate[l], vadd(vmul(br, o_r), vmul(bi, o_i)));
+        g_or[l] = vmul(br, sg[l]);
+        g_oi[l] = vmul(bi, sg[l]);
     }
-    float4 t0 = ld4(y0 + 256), t1 = ld4(y0 + 384), t2 = ld4(y0 + 512);
-    float4 gb00 = ld4(gb0), gb01 = ld4(gb0 + 128), gb02 = ld4(gb0 + 256);
-    g_gate[0] = f4mul(gb01, t1);
-    g_gate[1] = f4mul(gb02, t2);
-    float4 g_or[2], g_oi[2];
-#pragma unroll
-    for (int l = 0; l < 2; ++l) {
-        float4 o_r = f4sub(ld4(y1 + l * 128), ld4(y1 + 512 + 256 + l * 128));
-        float4 o_i = f4add(ld4(y1 + 512 + l * 128), ld4(y1 + 256 + l * 128));
-        float4 br = ld4(gb1 + l * 128), bi = ld4(gb1 + 256 + l * 128);
-        g_gate[l] = f4add(g_gate[l], f4add(f4mul(br, o_r), f4mul(bi, o_i)));
-        g_or[l] = f4mul(br, sg[l]);
-        g_oi[l] = f4mul(bi, sg[l]);
-    }
-    float4 p_r = f4sub(ld4(y2), ld4(y2 + 256 + 128));
-    float4 p_i = f4add(ld4(y2 + 256), ld4(y2 + 128));
-    float4 b2r = ld4(gb2), b2i = ld4(gb2 + 128);
-    g_gate[1] = f4add(g_gate[1], f4add(f4mul(b2r, p_r), f4mul(b2i, p_i)));
-    float4 g_pr = f4mul(b2r, sg[1]), g_pi = f4mul(b2i, sg[1]);
+    V p_r = vsub(Y2.ld4(y2), Y2.ld4(y2 + 256 + 128));
+    V p_i = vadd(Y2.ld4(y2 + 256), Y2.ld4(y2 + 128));
+    V b2r = gB2.ld4(gb2), b2i = gB2.ld4(gb2 + 128);
+    g_gate[1] = vadd(g_gate[1], vadd(vmul(b2r, p_r), vmul(b2i, p_i)));
+    V g_pr = vmul(b2r, sg[1]), g_pi = vmul(b2i, sg[1]);
 
     // ---- all reads done; writes (possibly in place)
-    float* o0 = gY0 + (long long)el * 640 + lane * 4;
-    float* o1 = gY1 + (long long)el * 1024 + lane * 4;
-    float* o2 = gY2 + (long long)el * 512 + lane * 4;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        float4 s = sg[l], gg = g_gate[l];
-        st4(o0 + l * 128, make_float4(gg.x * s.x * (1.f - s.x), gg.y * s.y * (1.f - s.y),
-                                      gg.z * s.z * (1.f - s.z), gg.w * s.w * (1.f - s.w)));
+        // sigma'(y) = s (1 - s)
+        V s = sg[l];
+        V ds = vsub(s, vmul(s, s));
+        gY0.st4(y0 + l * 128, vmul(g_gate[l], ds));
     }
-    st4(o0 + 256, make_float4(gb00.x * dsiluf_(t0.x), gb00.y * dsiluf_(t0.y), gb00.z * dsiluf_(t0.z), gb00.w * dsiluf_(t0.w)));
-    st4(o0 + 384, f4mul(gb01, sg[0]));
-    st4(o0 + 512, f4mul(gb02, sg[1]));
+    gY0.st4(y0 + 256, vmul(gb00, vdsilu(t0)));
+    gY0.st4(y0 + 384, vmul(gb01, sg[0]));
+    gY0.st4(y0 + 512, vmul(gb02, sg[1]));
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        st4(o1 + l * 128, g_or[l]);
-        st4(o1 + 256 + l * 128, g_oi[l]);
-        st4(o1 + 512 + l * 128, g_oi[l]);
-        st4(o1 + 512 + 256 + l * 128, f4scale(g_or[l], -1.f));
+        gY1.st4(y1 + l * 128, g_or[l]);
+        gY1.st4(y1 + 256 + l * 128, g_oi[l]);
+        gY1.st4(y1 + 512 + l * 128, g_oi[l]);
+        gY1.st4(y1 + 512 + 256 + l * 128, vneg(g_or[l]));
     }
-    st4(o2, g_pr);
-    st4(o2 + 128, g_pi);
-    st4(o2 + 256, g_pi);
-    st4(o2 + 256 + 128, f4scale(g_pr, -1.f));
+    gY2.st4(y2, g_pr);
+    gY2.st4(y2 + 128, g_pi);
+    gY2.st4(y2 + 256, g_pi);
+    gY2.st4(y2 + 256 + 128, vneg(g_pr));
 }
 
 // ------------------------------------------------------------------ rotate back + segmented reduce
 // MODE 0: message rows from the conv-2 outputs Z0/Z1/Z2.  MODE 1: edge-degree embedding, rows 0..2
 // from Z0 (= radial output [E,384]), rows 3..8 zero.
-template <int MODE>
-__device__ __forceinline__ void load_zl(const float* Z0, const float* Z1, const float* Z2, long long el, int lane, float4* zl) {
-    const float* z0 = Z0 + el * 384 + lane * 4;
+template <int MODE, class S, class V>
+__device__ __forceinline__ void load_zl(GP<S> Z0, GP<S> Z1, GP<S> Z2, long long el, int lane, V* zl) {
+    const long long z0 = el * 384 + lane * 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) zl[to_m(k)] = ld4(z0 + k * 128);
+    for (int k = 0; k < 3; ++k) zl[to_m(k)] = Z0.ld4(z0 + k * 128);
     if (MODE == 0) {
-        const float* z1 = Z1 + el * 1024 + lane * 4;
-        const float* z2 = Z2 + el * 512 + lane * 4;
+        const long long z1 = el * 1024 + lane * 4;
+        const long long z2 = el * 512 + lane * 4;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            zl[to_m(3 + l)] = f4sub(ld4(z1 + l * 128), ld4(z1 + 512 + 256 + l * 128));
-            zl[to_m(5 + l)] = f4add(ld4(z1 + 512 + l * 128), ld4(z1 + 256 + l * 128));
+            zl[to_m(3 + l)] = vsub(Z1.ld4(z1 + l * 128), Z1.ld4(z1 + 512 + 256 + l * 128));
+            zl[to_m(5 + l)] = vadd(Z1.ld4(z1 + 512 + l * 128), Z1.ld4(z1 + 256 + l * 128));
         }
-        zl[to_m(7)] = f4sub(ld4(z2), ld4(z2 + 256 + 128));
-        zl[to_m(8)] = f4add(ld4(z2 + 256), ld4(z2 + 128));
+        zl[to_m(7)] = vsub(Z2.ld4(z2), Z2.ld4(z2 + 256 + 128));
+        zl[to_m(8)] = vadd(Z2.ld4(z2 + 256), Z2.ld4(z2 + 128));
     } else {
 #pragma unroll
-        for (int k = 3; k < 9; ++k) zl[to_m(k)] = f4zero();
+        for (int k = 3; k < 9; ++k) zl[to_m(k)] = vzero<V>();
     }
 }
 
-template <int MODE>
+template <int MODE, class S>
 __global__ void __launch_bounds__(256)
-rotate_back_reduce_kernel(const float* __restrict__ Z0, const float* __restrict__ Z1, const float* __restrict__ Z2,
-                          const int* __restrict__ row_ptr, const float* __restrict__ wig,
-                          const float* __restrict__ env, float scale, long long e0, int node0, int n_nodes,
-                          const float* base, float* out) {   // base may alias out
+rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ row_ptr, GP<S> wig, GP<S> env,
+                          float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out) {   // base may alias out
+    using V = typename VecOf<S>::type;
     const int nl = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (nl >= n_nodes) return;
     const int i = node0 + nl;
-    float4 acc[9];
+    V acc[9];
 #pragma unroll
-    for (int r = 0; r < 9; ++r) acc[r] = f4zero();
+    for (int r = 0; r < 9; ++r) acc[r] = vzero<V>();
     for (long long e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
-        const WigReg w = load_wig(wig, e);
-        float4 zl[9], y[9];
-        load_zl<MODE>(Z0, Z1, Z2, e - e0, lane, zl);
+        const WigReg<S> w = load_wig<S>(wig, e);
+        V zl[9], y[9];
+        load_zl<MODE, S, V>(Z0, Z1, Z2, e - e0, lane, zl);
         rot_bwd(w, zl, y);
-        const float s = __ldg(env + e) * scale;
+        const S s = env.ld(e) * scale;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) f4fma(acc[r], s, y[r]);
+        for (int r = 0; r < 9; ++r) vfma(acc[r], s, y[r]);
     }
-    float* op = out + (long long)i * (9 * C) + lane * 4;
+    const long long op = (long long)i * (9 * C) + lane * 4;
     if (base) {
-        const float* bp = base + (long long)i * (9 * C) + lane * 4;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) st4(op + r * C, f4add(ld4(bp + r * C), acc[r]));
+        for (int r = 0; r < 9; ++r) out.st4(op + r * C, vadd(base.ld4(op + r * C), acc[r]));
     } else {
 #pragma unroll
-        for (int r = 0; r < 9; ++r) st4(op + r * C, acc[r]);
+        for (int r = 0; r < 9; ++r) out.st4(op + r * C, acc[r]);
     }
 }
 
 // adjoint, one warp per edge.  gZ* may alias Z*.
-template <int MODE>
+template <int MODE, class S>
 __global__ void __launch_bounds__(256)
-rotate_back_bwd_kernel(const float* Z0, const float* Z1, const float* Z2, const int* __restrict__ tgt,
-                       const float* __restrict__ wig, const float* __restrict__ env, float scale,
-                       long long e0, int n_e, const float* __restrict__ g_out,
-                       float* gZ0, float* gZ1, float* gZ2, float* __restrict__ g_env, float* __restrict__ g_wig) {
+rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
+                       long long e0, int n_e, GP<S> g_out, GP<S> gZ0, GP<S> gZ1, GP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
+    using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long e = e0 + el;
-    const WigReg w = load_wig(wig, e);
-    float4 zl[9], g[9], t[9];
-    load_zl<MODE>(Z0, Z1, Z2, el, lane, zl);
-    const float* gp = g_out + (long long)tgt[e] * (9 * C) + lane * 4;
+    const WigReg<S> w = load_wig<S>(wig, e);
+    V zl[9], g[9], t[9];
+    load_zl<MODE, S, V>(Z0, Z1, Z2, el, lane, zl);
+    const long long gp = (long long)tgt[e] * (9 * C) + lane * 4;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) g[r] = ld4(gp + r * C);
-    const float s = __ldg(env + e) * scale;
+    for (int r = 0; r < 9; ++r) g[r] = g_out.ld4(gp + r * C);
+    const S s = env.ld(e) * scale;
     // d/denv
     rot_bwd(w, zl, t);
-    float part = 0.f;
+    S part = cst<S>(0.f);
 #pragma unroll
-    for (int r = 0; r < 9; ++r) part += f4dot(t[r], g[r]);
+    for (int r = 0; r < 9; ++r) part = part + vdot(t[r], g[r]);
     part = warp_sum(part);
-    if (lane == 0) g_env[e] += scale * part;
+    if (lane == 0) g_env.st(e, g_env.ld(e) + part * scale);
     // d/dD[b][a] = s * sum_c zl[b][c] g[a][c]
-    float wacc[34];
+    S wacc[34];
 #pragma unroll
-    for (int q = 0; q < 34; ++q) wacc[q] = 0.f;
+    for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
     wig_outer_acc(wacc, zl, g);
     wig_grad_commit(wacc, s, g_wig, e, lane);
     // d/dz (m-primary rows) = s * (D g)[to_m(k)]
     rot_fwd(w, g, t);
-    float* o0 = gZ0 + (long long)el * 384 + lane * 4;
+    const long long o0 = (long long)el * 384 + lane * 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) st4(o0 + k * 128, f4scale(t[to_m(k)], s));
+    for (int k = 0; k < 3; ++k) gZ0.st4(o0 + k * 128, vscale(t[to_m(k)], s));
     if (MODE == 0) {
-        float* o1 = gZ1 + (long long)el * 1024 + lane * 4;
-        float* o2 = gZ2 + (long long)el * 512 + lane * 4;
+        const long long o1 = (long long)el * 1024 + lane * 4;
+        const long long o2 = (long long)el * 512 + lane * 4;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            float4 g_or = f4scale(t[to_m(3 + l)], s), g_oi = f4scale(t[to_m(5 + l)], s);
-            st4(o1 + l * 128, g_or);
-            st4(o1 + 256 + l * 128, g_oi);
-            st4(o1 + 512 + l * 128, g_oi);
-            st4(o1 + 512 + 256 + l * 128, f4scale(g_or, -1.f));
+            V g_or = vscale(t[to_m(3 + l)], s), g_oi = vscale(t[to_m(5 + l)], s);
+            gZ1.st4(o1 + l * 128, g_or);
+            gZ1.st4(o1 + 256 + l * 128, g_oi);
+            gZ1.st4(o1 + 512 + l * 128, g_oi);
+            gZ1.st4(o1 + 512 + 256 + l * 128, vneg(g_or));
         }
-        float4 g_pr = f4scale(t[to_m(7)], s), g_pi = f4scale(t[to_m(8)], s);
-        st4(o2, g_pr);
-        st4(o2 + 128, g_pi);
-        st4(o2 + 256, g_pi);
-        st4(o2 + 256 + 128, f4scale(g_pr, -1.f));
+        V g_pr = vscale(t[to_m(7)], s), g_pi = vscale(t[to_m(8)], s);
+        gZ2.st4(o2, g_pr);
+        gZ2.st4(o2 + 128, g_pi);
+        gZ2.st4(o2 + 256, g_pi);
+        gZ2.st4(o2 + 256 + 128, vneg(g_pr));
     }
 }
 
 }  // namespace
 
-void launch_gather_rotate_scale(const float* x, const int* src, const int* tgt, const float* wig, const float* rad,
-                                long long e0, int n_e, float* A0, float* A1, float* A2, cudaStream_t st) {
+template <class S>
+void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
+                                  GP<S> A0, GP<S> A1, GP<S> A2, cudaStream_t st) {
     if (n_e <= 0) return;
-    gather_rotate_scale_kernel<<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
     UMAB_LAUNCH_CHECK();
 }
-
-void launch_gather_rotate_bwd(const float* x, const int* row_ptr, const int* src, const float* wig, const float* rad,
-                              long long e0, int node0, int n_nodes, const float* gA0, const float* gA1,
-                              const float* gA2, float* g_rad, float* G, float* g_x, float* g_wig, cudaStream_t st) {
+template <class S>
+void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<S> wig, GP<S> rad, long long e0,
+                                int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, GP<S> g_rad, GP<S> G,
+                                GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
-    gather_rotate_bwd_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes,
-                                                                gA0, gA1, gA2, g_rad, G, g_x, g_wig);
+    gather_rotate_bwd_kernel<S><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
+                                                                   gA1, gA2, g_rad, G, g_x, g_wig);
     UMAB_LAUNCH_CHECK();
 }
-
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st) {
     if (n_nodes <= 0) return;
     source_reduce_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(G, sptr, sedge, n_nodes, g_x);
     UMAB_LAUNCH_CHECK();
 }
-
-void launch_combine_gate_fwd(const float* Y0, const float* Y1, const float* Y2, int n_e, float* B0, float* B1,
-                             float* B2, cudaStream_t st) {
+template <class S>
+void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B1, GP<S> B2, cudaStream_t st) {
     if (n_e <= 0) return;
-    combine_gate_fwd_kernel<<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
+    combine_gate_fwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
     UMAB_LAUNCH_CHECK();
 }
-
-void launch_combine_gate_bwd(const float* Y0, const float* Y1, const float* Y2, int n_e, const float* gB0,
-                             const float* gB1, const float* gB2, float* gY0, float* gY1, float* gY2, cudaStream_t st) {
+template <class S>
+void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, GP<S> gY0,
+                               GP<S> gY1, GP<S> gY2, cudaStream_t st) {
     if (n_e <= 0) return;
-    combine_gate_bwd_kernel<<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
+    combine_gate_bwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
     UMAB_LAUNCH_CHECK();
 }
-
-void launch_rotate_back_reduce(int mode, const float* Z0, const float* Z1, const float* Z2, const int* row_ptr,
-                               const float* wig, const float* env, float scale, long long e0, int node0,
-                               int n_nodes, const float* base, float* out, cudaStream_t st) {
+template <class S>
+void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* row_ptr, GP<S> wig, GP<S> env,
+                                 float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out,
+                                 cudaStream_t st) {
     if (n_nodes <= 0) return;
     dim3 grid((n_nodes + 7) / 8);
     if (mode == 0)
-        rotate_back_reduce_kernel<0><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
     else
-        rotate_back_reduce_kernel<1><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
     UMAB_LAUNCH_CHECK();
 }
-
-void launch_rotate_back_bwd(int mode, const float* Z0, const float* Z1, const float* Z2, const int* tgt,
-                            const float* wig, const float* env, float scale, long long e0, int n_e,
-                            const float* g_out, float* gZ0, float* gZ1, float* gZ2, float* g_env, float* g_wig,
-                            cudaStream_t st) {
+template <class S>
+void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* tgt, GP<S> wig, GP<S> env, float scale,
+                              long long e0, int n_e, GP<S> g_out, GP<S> gZ0, GP<S> gZ1, GP<S> gZ2, GP<S> g_env,
+                              GP<S> g_wig, cudaStream_t st) {
     if (n_e <= 0) return;
     dim3 grid((n_e + 7) / 8);
     if (mode == 0)
-        rotate_back_bwd_kernel<0><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+        rotate_back_bwd_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
     else
-        rotate_back_bwd_kernel<1><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+        rotate_back_bwd_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
     UMAB_LAUNCH_CHECK();
 }
+
+#define UMAB_INST(S)                                                                                                  \
+    template void launch_gather_rotate_scale_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, GP<S>,  \
+                                                  GP<S>, GP<S>, cudaStream_t);                                        \
+    template void launch_gather_rotate_bwd_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, int,      \
+                                                GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);       \
+    template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, cudaStream_t);           \
+    template void launch_combine_gate_bwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>,     \
+                                               cudaStream_t);                                                         \
+    template void launch_rotate_back_reduce_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long, \
+                                                 int, int, GP<S>, GP<S>, cudaStream_t);                               \
+    template void launch_rotate_back_bwd_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long,    \
+                                              int, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);
+UMAB_INST(float)
+UMAB_INST(D1)
+#undef UMAB_INST
 
 }  // namespace umab

@@ -18,7 +18,7 @@
 #include <vector>
 
 #include "../../include/umab.h"
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace umab {
 
@@ -64,6 +64,25 @@ struct DevBuf {
     int* i() const { return reinterpret_cast<int*>(p); }
 };
 long long DevBuf::total = 0;
+
+// a tensor of the pipeline: value plane + (Hessian path only) tangent plane
+struct TBuf {
+    DevBuf v, d;
+    template <class S> void ensure(size_t bytes) {
+        v.ensure(bytes);
+        if (std::is_same<S, D1>::value) d.ensure(bytes);
+    }
+    void release() { v.release(); d.release(); }
+};
+template <class S> GP<S> gp(const TBuf& b, long long off = 0);
+template <> GP<float> gp<float>(const TBuf& b, long long off) { return GP<float>{b.v.f() + off}; }
+template <> GP<D1> gp<D1>(const TBuf& b, long long off) { return GP<D1>{b.v.f() + off, b.d.f() + off}; }
+template <class S> GP<S> gnull();
+template <> GP<float> gnull<float>() { return GP<float>{nullptr}; }
+template <> GP<D1> gnull<D1>() { return GP<D1>{nullptr, nullptr}; }
+template <class S> constexpr int planes() { return std::is_same<S, D1>::value ? 2 : 1; }
+inline float* plane(const GP<float>& g, int) { return g.p; }
+inline float* plane(const GP<D1>& g, int k) { return k == 0 ? g.v : g.d; }
 
 struct Weight { DevBuf buf; size_t numel = 0; };
 
@@ -152,19 +171,20 @@ struct umab_engine {
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<Chunk> chunks;
     // geometry
-    DevBuf vec, dist, env, wig, gauss, g_gauss, g_env, g_wig, g_vec;
+    TBuf vec, dist, env, wig, gauss, g_gauss, g_env, g_wig, g_vec;
     // nodes
-    std::vector<DevBuf> xs, x1s, y1s, gps;
-    DevBuf nbuf, abuf, gx, gx1, gn, ggp, p1, s1, p2, gp2, gs1, node_e, Gbuf;
+    std::vector<TBuf> xs, x1s, y1s, gps;
+    TBuf nbuf, abuf, gx, gx1, gn, ggp, p1, s1, p2, gp2, gs1, Gbuf;
+    DevBuf node_e;
     // edge workspace
-    DevBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2;
+    TBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2;
     long long chunk_cap = 0;
     // store mode: conv-1 / conv-2 outputs of every layer are kept for the backward instead of being
     // recomputed (16.4 KB per edge and layer of HBM) when they fit `store_bytes`
-    std::vector<DevBuf> ystore, zstore;
+    std::vector<TBuf> ystore, zstore;
     bool store_mode = false;
     // host staging for umab_energy_forces_host
-    DevBuf e_dev, f_dev;
+    DevBuf e_dev, f_dev, t_dev, df_dev;
     // debug
     std::map<std::string, std::pair<DevBuf, size_t>> dbg;
     TcPlaneCache* tc_cache = tc_cache_create();       // bf16 planes of this engine's weights
@@ -251,25 +271,41 @@ struct umab_engine {
         }, /* algorithmic bytes: A and C once (+C again when accumulating), W once */
            4.0 * a.batch * ((double)a.M * a.K + (double)a.M * a.N * (a.accumulate ? 2 : 1)) + 4.0 * a.N * (double)a.K);
     }
-    void mm(const float* A, long long lda, const float* Wt, int N, int K, float* Cm, long long ldc, long long M,
+    // C = A W^T (+bias): value plane with the bias, tangent plane (Hessian path) without
+    template <class S>
+    void mm(GP<S> A, long long lda, const float* Wt, int N, int K, GP<S> Cm, long long ldc, long long M,
             const float* bias, int accumulate, cudaStream_t st) {
-        GemmArgs g;
-        g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.Cmat = Cm; g.ldc = ldc; g.bias = bias;
-        g.M = (int)M; g.N = N; g.K = K; g.accumulate = accumulate;
-        gemm(g, st);
+        for (int k = 0; k < planes<S>(); ++k) {
+            GemmArgs g;
+            g.A = plane(A, k); g.lda = lda; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
+            g.bias = k == 0 ? bias : nullptr;
+            g.M = (int)M; g.N = N; g.K = K; g.accumulate = accumulate;
+            gemm(g, st);
+        }
     }
     // per-coefficient SO(3) linear: rows (n, i) use weight l(i);  A [N,9,K] -> C [N,9,Nout]
-    void so3_mm(const float* A, int K, const float* Wt, int Nout, float* Cm, const float* bias, int accumulate,
+    template <class S>
+    void so3_mm(GP<S> A, int K, const float* Wt, int Nout, GP<S> Cm, const float* bias, int accumulate,
                 cudaStream_t st) {
-        GemmArgs g;
-        g.A = A; g.lda = 9LL * K; g.strideA = K;
-        g.W = Wt; g.ldw = K; g.strideW = (long long)Nout * K;
-        g.Cmat = Cm; g.ldc = 9LL * Nout; g.strideC = Nout;
-        g.bias = bias; g.bias_first_batch_only = 1;
-        g.M = n_nodes; g.N = Nout; g.K = K; g.batch = 9; g.accumulate = accumulate;
-        const int lsel[9] = {0, 1, 1, 1, 2, 2, 2, 2, 2};
-        for (int i = 0; i < 9; ++i) g.wsel[i] = lsel[i];
-        gemm(g, st);
+        for (int k = 0; k < planes<S>(); ++k) {
+            GemmArgs g;
+            g.A = plane(A, k); g.lda = 9LL * K; g.strideA = K;
+            g.W = Wt; g.ldw = K; g.strideW = (long long)Nout * K;
+            g.Cmat = plane(Cm, k); g.ldc = 9LL * Nout; g.strideC = Nout;
+            g.bias = k == 0 ? bias : nullptr; g.bias_first_batch_only = 1;
+            g.M = n_nodes; g.N = Nout; g.K = K; g.batch = 9; g.accumulate = accumulate;
+            const int lsel[9] = {0, 1, 1, 1, 2, 2, 2, 2, 2};
+            for (int i = 0; i < 9; ++i) g.wsel[i] = lsel[i];
+            gemm(g, st);
+        }
+    }
+    template <class S> void zero(const TBuf& b, size_t bytes, cudaStream_t st) {
+        UMAB_CUDA(cudaMemsetAsync(b.v.p, 0, bytes, st));
+        if (std::is_same<S, D1>::value) UMAB_CUDA(cudaMemsetAsync(b.d.p, 0, bytes, st));
+    }
+    template <class S> void copy(const TBuf& dst, const TBuf& srcb, size_t bytes, cudaStream_t st) {
+        UMAB_CUDA(cudaMemcpyAsync(dst.v.p, srcb.v.p, bytes, cudaMemcpyDeviceToDevice, st));
+        if (std::is_same<S, D1>::value) UMAB_CUDA(cudaMemcpyAsync(dst.d.p, srcb.d.p, bytes, cudaMemcpyDeviceToDevice, st));
     }
     void save_dbg(const std::string& name, const void* p, size_t numel, cudaStream_t st) {
         if (!cfg.debug) return;
@@ -311,12 +347,11 @@ struct umab_engine {
         odeg.ensure(sizeof(int) * n_nodes); sptr.ensure(sizeof(int) * (n_nodes + 1)); cursor.ensure(sizeof(int) * n_nodes);
         stmp.ensure(sizeof(int) * ne); sedge.ensure(sizeof(int) * ne);
         launch_source_csr(src.i(), (int)n_edges, n_nodes, odeg.i(), sptr.i(), cursor.i(), stmp.i(), sedge.i(), st);
-        plan_chunks();
     }
 
-    void plan_chunks() {
+    template <class S> void plan_chunks() {
         long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (32LL << 30);
-        long long cap = std::max<long long>(budget / (long long)(EDGE_WS_FLOATS * 4), 1024);
+        long long cap = std::max<long long>(budget / (long long)(EDGE_WS_FLOATS * 4 * planes<S>()), 1024);
         chunks.clear();
         int node0 = 0;
         long long biggest = 0;
@@ -332,111 +367,110 @@ struct umab_engine {
         }
         chunk_cap = std::max<long long>(biggest, 1);
         size_t f = sizeof(float) * (size_t)chunk_cap;
-        wA.ensure(f * 2304); wY.ensure(f * 2176); wB.ensure(f * 1152); wZ.ensure(f * 1920); wRAD.ensure(f * 1536);
-        wU1.ensure(f * 128); wH1.ensure(f * 128); wU2.ensure(f * 128); wH2.ensure(f * 128);
+        wA.ensure<S>(f * 2304); wY.ensure<S>(f * 2176); wB.ensure<S>(f * 1152); wZ.ensure<S>(f * 1920);
+        wRAD.ensure<S>(f * 1536);
+        wU1.ensure<S>(f * 128); wH1.ensure<S>(f * 128); wU2.ensure<S>(f * 128); wH2.ensure<S>(f * 128);
     }
 
     // ------------------------------------------------------------------ edge stages
-    float* A0() { return wA.f(); }
-    float* A1() { return wA.f() + chunk_cap * 768; }
-    float* A2() { return wA.f() + chunk_cap * (768 + 1024); }
-    float* Y0() { return wY.f(); }
-    float* Y1() { return wY.f() + chunk_cap * 640; }
-    float* Y2() { return wY.f() + chunk_cap * (640 + 1024); }
-    float* B0() { return wB.f(); }
-    float* B1() { return wB.f() + chunk_cap * 384; }
-    float* B2() { return wB.f() + chunk_cap * (384 + 512); }
-    float* Z0() { return wZ.f(); }
-    float* Z1() { return wZ.f() + chunk_cap * 384; }
-    float* Z2() { return wZ.f() + chunk_cap * (384 + 1024); }
-
-    struct YZ { float *y0, *y1, *y2, *z0, *z1, *z2; };
-    YZ yz_for(int layer, const Chunk& c) {
+    template <class S> struct EB { GP<S> a0, a1, a2, b0, b1, b2, y0, y1, y2, z0, z1, z2, rad, u1, h1, u2, h2; };
+    template <class S> EB<S> bufs_for(int layer, const Chunk& c) {
+        EB<S> b;
+        const long long cc = chunk_cap;
+        b.a0 = gp<S>(wA); b.a1 = gp<S>(wA, cc * 768); b.a2 = gp<S>(wA, cc * (768 + 1024));
+        b.b0 = gp<S>(wB); b.b1 = gp<S>(wB, cc * 384); b.b2 = gp<S>(wB, cc * (384 + 512));
         if (store_mode && layer >= 0) {
-            float* yb = ystore[layer].f();
-            float* zb = zstore[layer].f();
             const long long E = n_edges;
-            return {yb + c.e0 * 640, yb + E * 640 + c.e0 * 1024, yb + E * 1664 + c.e0 * 512,
-                    zb + c.e0 * 384, zb + E * 384 + c.e0 * 1024, zb + E * 1408 + c.e0 * 512};
+            b.y0 = gp<S>(ystore[layer], c.e0 * 640); b.y1 = gp<S>(ystore[layer], E * 640 + c.e0 * 1024);
+            b.y2 = gp<S>(ystore[layer], E * 1664 + c.e0 * 512);
+            b.z0 = gp<S>(zstore[layer], c.e0 * 384); b.z1 = gp<S>(zstore[layer], E * 384 + c.e0 * 1024);
+            b.z2 = gp<S>(zstore[layer], E * 1408 + c.e0 * 512);
+        } else {
+            b.y0 = gp<S>(wY); b.y1 = gp<S>(wY, cc * 640); b.y2 = gp<S>(wY, cc * (640 + 1024));
+            b.z0 = gp<S>(wZ); b.z1 = gp<S>(wZ, cc * 384); b.z2 = gp<S>(wZ, cc * (384 + 1024));
         }
-        return {Y0(), Y1(), Y2(), Z0(), Z1(), Z2()};
+        b.rad = gp<S>(wRAD); b.u1 = gp<S>(wU1); b.h1 = gp<S>(wH1); b.u2 = gp<S>(wU2); b.h2 = gp<S>(wH2);
+        return b;
     }
 
-    void radial_fwd(const RadialW& r, const Chunk& c, cudaStream_t st) {
+    template <class S> void radial_fwd(const RadialW& r, const Chunk& c, const EB<S>& b, cudaStream_t st) {
         const long long e0 = c.e0;
-        mm(gauss.f() + e0 * NB, NB, r.w1g, 128, NB, wU1.f(), 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_fwd(wU1.f(), wH1.f(), r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st);
-        mm(wH1.f(), 128, r.w2, 128, 128, wU2.f(), 128, c.n_e, r.b2, 0, st);
-        launch_ln_silu_fwd(wU2.f(), wH2.f(), r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st);
-        mm(wH2.f(), 128, r.w3, r.n_out, 128, wRAD.f(), r.n_out, c.n_e, r.b3, 0, st);
+        mm<S>(gp<S>(gauss, e0 * NB), NB, r.w1g, 128, NB, b.u1, 128, c.n_e, nullptr, 0, st);
+        launch_ln_silu_fwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st);
+        mm<S>(b.h1, 128, r.w2, 128, 128, b.u2, 128, c.n_e, r.b2, 0, st);
+        launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st);
+        mm<S>(b.h2, 128, r.w3, r.n_out, 128, b.rad, r.n_out, c.n_e, r.b3, 0, st);
     }
     // g_rad lives in wRAD [n_e, n_out]; accumulates into g_gauss
-    void radial_bwd(const RadialW& r, const Chunk& c, cudaStream_t st) {
-        mm(wRAD.f(), r.n_out, r.w3_t, 128, r.n_out, wH2.f(), 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_bwd(wU2.f(), wH2.f(), r.ln2w, r.ln2b, c.n_e, st);
-        mm(wH2.f(), 128, r.w2_t, 128, 128, wH1.f(), 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_bwd(wU1.f(), wH1.f(), r.ln1w, r.ln1b, c.n_e, st);
-        mm(wH1.f(), 128, r.w1g_t, NB, 128, g_gauss.f() + c.e0 * NB, NB, c.n_e, nullptr, 1, st);
+    template <class S> void radial_bwd(const RadialW& r, const Chunk& c, const EB<S>& b, cudaStream_t st) {
+        mm<S>(b.rad, r.n_out, r.w3_t, 128, r.n_out, b.h2, 128, c.n_e, nullptr, 0, st);
+        launch_ln_silu_bwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, c.n_e, st);
+        mm<S>(b.h2, 128, r.w2_t, 128, 128, b.h1, 128, c.n_e, nullptr, 0, st);
+        launch_ln_silu_bwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, c.n_e, st);
+        mm<S>(b.h1, 128, r.w1g_t, NB, 128, gp<S>(g_gauss, c.e0 * NB), NB, c.n_e, nullptr, 1, st);
     }
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)
-    void edge_fwd_chunk(const LayerW& w, const float* n1, const Chunk& c, int layer, bool dbg_on, cudaStream_t st) {
-        const YZ b = yz_for(layer, c);
-        radial_fwd(w.rad, c, st);
-        timed(P_GATHER, c.n_e * 15512.0 + c.n_nodes * 4608.0, st, [&] {
-            launch_gather_rotate_scale(n1, src.i(), tgt.i(), wig.f(), wRAD.f(), c.e0, c.n_e, A0(), A1(), A2(), st); });
-        mm(A0(), 768, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, 0, st);
-        mm(A1(), 512, w.c1m1, 512, 512, b.y1, 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(A2(), 256, w.c1m2, 256, 256, b.y2, 256, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_COMBINE, c.n_e * 13312.0, st, [&] { launch_combine_gate_fwd(b.y0, b.y1, b.y2, c.n_e, B0(), B1(), B2(), st); });
-        mm(B0(), 384, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, 0, st);
-        mm(B1(), 256, w.c2m1, 512, 256, b.z1, 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(B2(), 128, w.c2m2, 256, 128, b.z2, 256, 2LL * c.n_e, nullptr, 0, st);
+    template <class S>
+    void edge_fwd_chunk(const LayerW& w, GP<S> n1, const Chunk& c, int layer, bool dbg_on, cudaStream_t st) {
+        const EB<S> b = bufs_for<S>(layer, c);
+        const double P = planes<S>();
+        radial_fwd<S>(w.rad, c, b, st);
+        timed(P_GATHER, P * (c.n_e * 15512.0 + c.n_nodes * 4608.0), st, [&] {
+            launch_gather_rotate_scale_t<S>(n1, src.i(), tgt.i(), gp<S>(wig), b.rad, c.e0, c.n_e, b.a0, b.a1, b.a2, st); });
+        mm<S>(b.a0, 768, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, 0, st);
+        mm<S>(b.a1, 512, w.c1m1, 512, 512, b.y1, 512, 2LL * c.n_e, nullptr, 0, st);
+        mm<S>(b.a2, 256, w.c1m2, 256, 256, b.y2, 256, 2LL * c.n_e, nullptr, 0, st);
+        timed(P_COMBINE, P * c.n_e * 13312.0, st, [&] {
+            launch_combine_gate_fwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, st); });
+        mm<S>(b.b0, 384, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, 0, st);
+        mm<S>(b.b1, 256, w.c2m1, 512, 256, b.z1, 512, 2LL * c.n_e, nullptr, 0, st);
+        mm<S>(b.b2, 128, w.c2m2, 256, 128, b.z2, 256, 2LL * c.n_e, nullptr, 0, st);
         if (dbg_on && chunks.size() == 1) {
             std::string p = "l" + std::to_string(layer) + ".";
-            save_dbg(p + "rad", wRAD.f(), (size_t)c.n_e * 1536, st);
-            save_dbg(p + "a0", A0(), (size_t)c.n_e * 768, st);
-            save_dbg(p + "a1", A1(), (size_t)c.n_e * 1024, st);
-            save_dbg(p + "a2", A2(), (size_t)c.n_e * 512, st);
-            save_dbg(p + "y0", b.y0, (size_t)c.n_e * 640, st);
-            save_dbg(p + "y1", b.y1, (size_t)c.n_e * 1024, st);
-            save_dbg(p + "y2", b.y2, (size_t)c.n_e * 512, st);
-            save_dbg(p + "z0", b.z0, (size_t)c.n_e * 384, st);
-            save_dbg(p + "z1", b.z1, (size_t)c.n_e * 1024, st);
-            save_dbg(p + "z2", b.z2, (size_t)c.n_e * 512, st);
+            save_dbg(p + "rad", plane(b.rad, 0), (size_t)c.n_e * 1536, st);
+            save_dbg(p + "y0", plane(b.y0, 0), (size_t)c.n_e * 640, st);
+            save_dbg(p + "y1", plane(b.y1, 0), (size_t)c.n_e * 1024, st);
+            save_dbg(p + "y2", plane(b.y2, 0), (size_t)c.n_e * 512, st);
+            save_dbg(p + "z0", plane(b.z0, 0), (size_t)c.n_e * 384, st);
         }
     }
-    void edge_bwd_chunk(const LayerW& w, const float* n1, const Chunk& c, int layer, const float* g_out, float* g_n1,
-                        cudaStream_t st) {
-        const YZ b = yz_for(layer, c);
-        if (store_mode) radial_fwd(w.rad, c, st);            // only the radial weights are recomputed
-        else edge_fwd_chunk(w, n1, c, layer, false, st);     // recompute everything up to Z
-        timed(P_ROTBACK_BWD, c.n_e * (2 * 7680.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0, st, [&] {
-            launch_rotate_back_bwd(0, b.z0, b.z1, b.z2, tgt.i(), wig.f(), env.f(), 1.0f, c.e0, c.n_e, g_out,
-                                   b.z0, b.z1, b.z2, g_env.f(), g_wig.f(), st); });
-        mm(b.z0, 384, w.c2m0_t, 384, 384, B0(), 384, c.n_e, nullptr, 0, st);
-        mm(b.z1, 512, w.c2m1_t, 256, 512, B1(), 256, 2LL * c.n_e, nullptr, 0, st);
-        mm(b.z2, 256, w.c2m2_t, 128, 256, B2(), 128, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_COMBINE_BWD, c.n_e * (8704.0 * 2 + 4608.0), st, [&] {
-            launch_combine_gate_bwd(b.y0, b.y1, b.y2, c.n_e, B0(), B1(), B2(), b.y0, b.y1, b.y2, st); });
-        mm(b.y0, 640, w.c1m0_t, 768, 640, A0(), 768, c.n_e, nullptr, 0, st);
-        mm(b.y1, 512, w.c1m1_t, 512, 512, A1(), 512, 2LL * c.n_e, nullptr, 0, st);
-        mm(b.y2, 256, w.c1m2_t, 256, 256, A2(), 256, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_GATHER_BWD, c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0, st, [&] {
-            launch_gather_rotate_bwd(n1, row_ptr.i(), src.i(), wig.f(), wRAD.f(), c.e0, c.node0, c.n_nodes, A0(), A1(), A2(),
-                                     wRAD.f(), Gbuf.f(), g_n1, g_wig.f(), st); });
-        radial_bwd(w.rad, c, st);
+    template <class S>
+    void edge_bwd_chunk(const LayerW& w, GP<S> n1, const Chunk& c, int layer, GP<S> g_out, GP<S> g_n1, cudaStream_t st) {
+        const EB<S> b = bufs_for<S>(layer, c);
+        const double P = planes<S>();
+        if (store_mode) radial_fwd<S>(w.rad, c, b, st);          // only the radial weights are recomputed
+        else edge_fwd_chunk<S>(w, n1, c, layer, false, st);      // recompute everything up to Z
+        timed(P_ROTBACK_BWD, P * (c.n_e * (2 * 7680.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
+            launch_rotate_back_bwd_t<S>(0, b.z0, b.z1, b.z2, tgt.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0, c.n_e, g_out,
+                                        b.z0, b.z1, b.z2, gp<S>(g_env), gp<S>(g_wig), st); });
+        mm<S>(b.z0, 384, w.c2m0_t, 384, 384, b.b0, 384, c.n_e, nullptr, 0, st);
+        mm<S>(b.z1, 512, w.c2m1_t, 256, 512, b.b1, 256, 2LL * c.n_e, nullptr, 0, st);
+        mm<S>(b.z2, 256, w.c2m2_t, 128, 256, b.b2, 128, 2LL * c.n_e, nullptr, 0, st);
+        timed(P_COMBINE_BWD, P * c.n_e * (8704.0 * 2 + 4608.0), st, [&] {
+            launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, b.y0, b.y1, b.y2, st); });
+        mm<S>(b.y0, 640, w.c1m0_t, 768, 640, b.a0, 768, c.n_e, nullptr, 0, st);
+        mm<S>(b.y1, 512, w.c1m1_t, 512, 512, b.a1, 512, 2LL * c.n_e, nullptr, 0, st);
+        mm<S>(b.y2, 256, w.c1m2_t, 256, 256, b.a2, 256, 2LL * c.n_e, nullptr, 0, st);
+        timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0), st, [&] {
+            launch_gather_rotate_bwd_t<S>(n1, row_ptr.i(), src.i(), gp<S>(wig), b.rad, c.e0, c.node0, c.n_nodes, b.a0, b.a1,
+                                          b.a2, b.rad, gp<S>(Gbuf), g_n1, gp<S>(g_wig), st); });
+        radial_bwd<S>(w.rad, c, b, st);
     }
 
     // ------------------------------------------------------------------ full evaluation
-    void evaluate(const float* pos, int nimg, double* energy_dev, float* forces_dev, cudaStream_t st) {
+    // S = float: energies + forces.  S = D1: positions carry a tangent (displacement direction);
+    // forces.d then is d(forces)/d(eps) = -H.t, one analytic Hessian column per image.
+    template <class S>
+    void evaluate(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
         if (!finalized) throw CudaError("umab_finalize_weights has not been called");
-        timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(pos, nimg, st); });
+        timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(plane(pos, 0), nimg, st); });
+        plan_chunks<S>();
         const int L = cfg.num_layers;
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
-        const bool want_f = forces_dev != nullptr;
+        const bool want_f = (bool)forces;
         {
-            const double need = (double)n_edges * 4096.0 * 4.0 * L;
+            const double need = (double)n_edges * 4096.0 * 4.0 * L * planes<S>();
             double budget = (double)cfg.store_bytes;
             if (cfg.store_bytes == 0) {
                 size_t fr = 0, tot = 0;
@@ -446,122 +480,132 @@ struct umab_engine {
             store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
             if (store_mode) {
                 ystore.resize(L); zstore.resize(L);
-                for (auto& b : ystore) b.ensure(ne * 2176 * 4);
-                for (auto& b : zstore) b.ensure(ne * 1920 * 4);
+                for (auto& b : ystore) b.ensure<S>(ne * 2176 * 4);
+                for (auto& b : zstore) b.ensure<S>(ne * 1920 * 4);
             }
         }
-        vec.ensure(ne * 12); dist.ensure(ne * 4); env.ensure(ne * 4); wig.ensure(ne * WIG * 4); gauss.ensure(ne * NB * 4);
-        timed(P_GEOMETRY, (double)n_edges * (24.0 + 4.0 * (5 + WIG + NB)), st, [&] {
-            launch_geometry_fwd(pos, src.i(), tgt.i(), (int)n_edges, cfg.cutoff, vec.f(), dist.f(), env.f(), wig.f(), gauss.f(), st); });
+        vec.ensure<S>(ne * 12); dist.ensure<S>(ne * 4); env.ensure<S>(ne * 4); wig.ensure<S>(ne * WIG * 4);
+        gauss.ensure<S>(ne * NB * 4);
+        timed(P_GEOMETRY, planes<S>() * (double)n_edges * (24.0 + 4.0 * (5 + WIG + NB)), st, [&] {
+            launch_geometry_fwd_t<S>(pos, src.i(), tgt.i(), (int)n_edges, cfg.cutoff, gp<S>(vec), gp<S>(dist), gp<S>(env),
+                                     gp<S>(wig), gp<S>(gauss), st); });
         xs.resize(L + 1); x1s.resize(L); y1s.resize(L); gps.resize(L);
-        for (auto& b : xs) b.ensure(nf);
-        for (auto& b : x1s) b.ensure(nf);
-        for (auto& b : y1s) b.ensure(nf);
-        for (auto& b : gps) b.ensure((size_t)n_nodes * 2 * H * 4);
-        nbuf.ensure(nf); abuf.ensure(nf);
-        p1.ensure((size_t)n_nodes * H * 4); s1.ensure((size_t)n_nodes * H * 4); p2.ensure((size_t)n_nodes * H * 4);
+        for (auto& b : xs) b.ensure<S>(nf);
+        for (auto& b : x1s) b.ensure<S>(nf);
+        for (auto& b : y1s) b.ensure<S>(nf);
+        for (auto& b : gps) b.ensure<S>((size_t)n_nodes * 2 * H * 4);
+        nbuf.ensure<S>(nf); abuf.ensure<S>(nf);
+        p1.ensure<S>((size_t)n_nodes * H * 4); s1.ensure<S>((size_t)n_nodes * H * 4); p2.ensure<S>((size_t)n_nodes * H * 4);
         node_e.ensure((size_t)n_nodes * 4);
 
-        // ---- embedding + edge-degree embedding
-        launch_embed(sphere_emb, csd, zt.i(), n_nodes, xs[0].f(), st);
+        // ---- embedding (position independent: zero tangent) + edge-degree embedding
+        launch_embed(sphere_emb, csd, zt.i(), n_nodes, xs[0].v.f(), st);
+        if (std::is_same<S, D1>::value) UMAB_CUDA(cudaMemsetAsync(xs[0].d.p, 0, nf, st));
         for (const Chunk& c : chunks) {
-            radial_fwd(ed_rad, c, st);
-            launch_rotate_back_reduce(1, wRAD.f(), nullptr, nullptr, row_ptr.i(), wig.f(), env.f(),
-                                      1.0f / cfg.edge_degree_rescale, c.e0, c.node0, c.n_nodes, xs[0].f(), xs[0].f(), st);
+            const EB<S> b = bufs_for<S>(-1, c);
+            radial_fwd<S>(ed_rad, c, b, st);
+            launch_rotate_back_reduce_t<S>(1, b.rad, gnull<S>(), gnull<S>(), row_ptr.i(), gp<S>(wig), gp<S>(env),
+                                           1.0f / cfg.edge_degree_rescale, c.e0, c.node0, c.n_nodes, gp<S>(xs[0]),
+                                           gp<S>(xs[0]), st);
         }
-        save_dbg("x0", xs[0].p, (size_t)n_nodes * 9 * C, st);
-        save_dbg("gauss", gauss.p, (size_t)n_edges * NB, st);
-        save_dbg("wig", wig.p, (size_t)n_edges * WIG, st);
-        save_dbg("env", env.p, (size_t)n_edges, st);
+        save_dbg("x0", xs[0].v.p, (size_t)n_nodes * 9 * C, st);
+        save_dbg("gauss", gauss.v.p, (size_t)n_edges * NB, st);
+        save_dbg("wig", wig.v.p, (size_t)n_edges * WIG, st);
+        save_dbg("env", env.v.p, (size_t)n_edges, st);
 
         // ---- layers
         for (int l = 0; l < L; ++l) {
             const LayerW& w = layers[l];
-            launch_rms_fwd(xs[l].f(), w.n1w, w.n1b, csd, n_nodes, nbuf.f(), st);
-            save_dbg("l" + std::to_string(l) + ".n1", nbuf.p, (size_t)n_nodes * 9 * C, st);
+            launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);
+            save_dbg("l" + std::to_string(l) + ".n1", nbuf.v.p, (size_t)n_nodes * 9 * C, st);
             for (const Chunk& c : chunks) {
-                edge_fwd_chunk(w, nbuf.f(), c, l, true, st);
-                const YZ b = yz_for(l, c);
-                timed(P_ROTBACK, c.n_e * 7828.0 + c.n_nodes * 9216.0, st, [&] {
-                    launch_rotate_back_reduce(0, b.z0, b.z1, b.z2, row_ptr.i(), wig.f(), env.f(), 1.0f, c.e0, c.node0,
-                                              c.n_nodes, xs[l].f(), x1s[l].f(), st); });
+                edge_fwd_chunk<S>(w, gp<S>(nbuf), c, l, true, st);
+                const EB<S> b = bufs_for<S>(l, c);
+                timed(P_ROTBACK, planes<S>() * (c.n_e * 7828.0 + c.n_nodes * 9216.0), st, [&] {
+                    launch_rotate_back_reduce_t<S>(0, b.z0, b.z1, b.z2, row_ptr.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0,
+                                                   c.node0, c.n_nodes, gp<S>(xs[l]), gp<S>(x1s[l]), st); });
             }
-            save_dbg("l" + std::to_string(l) + ".x1", x1s[l].p, (size_t)n_nodes * 9 * C, st);
-            launch_rms_fwd(x1s[l].f(), w.n2w, w.n2b, nullptr, n_nodes, nbuf.f(), st);
-            mm(nbuf.f(), 9LL * C, w.smlp, 2 * H, C, gps[l].f(), 2 * H, n_nodes, w.smlp_b, 0, st);
-            so3_mm(nbuf.f(), C, w.so3_1, H, y1s[l].f(), w.so3_1_b, 0, st);
-            launch_ffn_gate_fwd(y1s[l].f(), gps[l].f(), n_nodes, abuf.f(), st);
-            UMAB_CUDA(cudaMemcpyAsync(xs[l + 1].p, x1s[l].p, nf, cudaMemcpyDeviceToDevice, st));
-            so3_mm(abuf.f(), H, w.so3_2, C, xs[l + 1].f(), w.so3_2_b, 1, st);
-            save_dbg("l" + std::to_string(l) + ".x", xs[l + 1].p, (size_t)n_nodes * 9 * C, st);
+            save_dbg("l" + std::to_string(l) + ".x1", x1s[l].v.p, (size_t)n_nodes * 9 * C, st);
+            launch_rms_fwd_t<S>(gp<S>(x1s[l]), w.n2w, w.n2b, nullptr, n_nodes, gp<S>(nbuf), st);
+            mm<S>(gp<S>(nbuf), 9LL * C, w.smlp, 2 * H, C, gp<S>(gps[l]), 2 * H, n_nodes, w.smlp_b, 0, st);
+            so3_mm<S>(gp<S>(nbuf), C, w.so3_1, H, gp<S>(y1s[l]), w.so3_1_b, 0, st);
+            launch_ffn_gate_fwd_t<S>(gp<S>(y1s[l]), gp<S>(gps[l]), n_nodes, gp<S>(abuf), st);
+            copy<S>(xs[l + 1], x1s[l], nf, st);
+            so3_mm<S>(gp<S>(abuf), H, w.so3_2, C, gp<S>(xs[l + 1]), w.so3_2_b, 1, st);
+            save_dbg("l" + std::to_string(l) + ".x", xs[l + 1].v.p, (size_t)n_nodes * 9 * C, st);
         }
         // ---- head
-        launch_rms_fwd(xs[L].f(), normw, normb, nullptr, n_nodes, nbuf.f(), st);
-        mm(nbuf.f(), 9LL * C, h0, H, C, p1.f(), H, n_nodes, h0_b, 0, st);
-        launch_eltwise(0, p1.f(), nullptr, (long long)n_nodes * H, s1.f(), st);
-        mm(s1.f(), H, h2, H, H, p2.f(), H, n_nodes, h2_b, 0, st);
-        if (want_f) gp2.ensure((size_t)n_nodes * H * 4);
-        launch_head_final(p2.f(), h4, h4_b, n_nodes, node_e.f(), want_f ? gp2.f() : nullptr, st);
-        launch_energy_reduce(node_e.f(), n_img, n_atoms, energy_dev, st);
+        launch_rms_fwd_t<S>(gp<S>(xs[L]), normw, normb, nullptr, n_nodes, gp<S>(nbuf), st);
+        mm<S>(gp<S>(nbuf), 9LL * C, h0, H, C, gp<S>(p1), H, n_nodes, h0_b, 0, st);
+        launch_eltwise_t<S>(0, gp<S>(p1), gnull<S>(), (long long)n_nodes * H, gp<S>(s1), st);
+        mm<S>(gp<S>(s1), H, h2, H, H, gp<S>(p2), H, n_nodes, h2_b, 0, st);
+        if (want_f) gp2.ensure<S>((size_t)n_nodes * H * 4);
+        launch_head_final_t<S>(gp<S>(p2), h4, h4_b, n_nodes, node_e.f(), want_f ? gp<S>(gp2) : gnull<S>(), st);
+        if (energy_dev) launch_energy_reduce(node_e.f(), n_img, n_atoms, energy_dev, st);
         save_dbg("node_e", node_e.p, (size_t)n_nodes, st);
         if (!want_f) return;
 
         // ================= backward: dE_total/dpos
-        gx.ensure(nf); gx1.ensure(nf); gn.ensure(nf); ggp.ensure((size_t)n_nodes * 2 * H * 4);
-        gs1.ensure((size_t)n_nodes * H * 4);
-        Gbuf.ensure(ne * 9 * C * 4);
-        g_gauss.ensure(ne * NB * 4); g_env.ensure(ne * 4); g_wig.ensure(ne * WIG * 4); g_vec.ensure(ne * 12);
-        UMAB_CUDA(cudaMemsetAsync(g_gauss.p, 0, ne * NB * 4, st));
-        UMAB_CUDA(cudaMemsetAsync(g_env.p, 0, ne * 4, st));
-        UMAB_CUDA(cudaMemsetAsync(g_wig.p, 0, ne * WIG * 4, st));
+        gx.ensure<S>(nf); gx1.ensure<S>(nf); gn.ensure<S>(nf); ggp.ensure<S>((size_t)n_nodes * 2 * H * 4);
+        gs1.ensure<S>((size_t)n_nodes * H * 4);
+        Gbuf.ensure<S>(ne * 9 * C * 4);
+        g_gauss.ensure<S>(ne * NB * 4); g_env.ensure<S>(ne * 4); g_wig.ensure<S>(ne * WIG * 4); g_vec.ensure<S>(ne * 12);
+        zero<S>(g_gauss, ne * NB * 4, st);
+        zero<S>(g_env, ne * 4, st);
+        zero<S>(g_wig, ne * WIG * 4, st);
 
-        mm(gp2.f(), H, h2_t, H, H, gs1.f(), H, n_nodes, nullptr, 0, st);
-        launch_eltwise(1, gs1.f(), p1.f(), (long long)n_nodes * H, gs1.f(), st);      // g_p1
-        UMAB_CUDA(cudaMemsetAsync(gn.p, 0, nf, st));
-        mm(gs1.f(), H, h0_t, C, H, gn.f(), 9LL * C, n_nodes, nullptr, 0, st);         // g_xf (row 0 only)
-        launch_rms_bwd(xs[L].f(), normw, gn.f(), nullptr, n_nodes, gx.f(), st);
+        mm<S>(gp<S>(gp2), H, h2_t, H, H, gp<S>(gs1), H, n_nodes, nullptr, 0, st);
+        launch_eltwise_t<S>(1, gp<S>(gs1), gp<S>(p1), (long long)n_nodes * H, gp<S>(gs1), st);      // g_p1
+        zero<S>(gn, nf, st);
+        mm<S>(gp<S>(gs1), H, h0_t, C, H, gp<S>(gn), 9LL * C, n_nodes, nullptr, 0, st);             // g_xf (row 0 only)
+        launch_rms_bwd_t<S>(gp<S>(xs[L]), normw, gp<S>(gn), gnull<S>(), n_nodes, gp<S>(gx), st);
         for (int l = L - 1; l >= 0; --l) {
             const LayerW& w = layers[l];
             // FFN adjoint (dL/dy2 = gx)
-            so3_mm(gx.f(), C, w.so3_2_t, H, abuf.f(), nullptr, 0, st);                 // g_a
-            launch_ffn_gate_bwd(y1s[l].f(), gps[l].f(), abuf.f(), n_nodes, abuf.f(), ggp.f(), st);   // g_y1, g_gp
-            so3_mm(abuf.f(), H, w.so3_1_t, C, gn.f(), nullptr, 0, st);                 // g_n2
-            mm(ggp.f(), 2 * H, w.smlp_t, C, 2 * H, gn.f(), 9LL * C, n_nodes, nullptr, 1, st);
-            launch_rms_bwd(x1s[l].f(), w.n2w, gn.f(), gx.f(), n_nodes, gx1.f(), st);   // g_x1 = gx + norm2^T g_n2
+            so3_mm<S>(gp<S>(gx), C, w.so3_2_t, H, gp<S>(abuf), nullptr, 0, st);                     // g_a
+            launch_ffn_gate_bwd_t<S>(gp<S>(y1s[l]), gp<S>(gps[l]), gp<S>(abuf), n_nodes, gp<S>(abuf), gp<S>(ggp), st);
+            so3_mm<S>(gp<S>(abuf), H, w.so3_1_t, C, gp<S>(gn), nullptr, 0, st);                     // g_n2
+            mm<S>(gp<S>(ggp), 2 * H, w.smlp_t, C, 2 * H, gp<S>(gn), 9LL * C, n_nodes, nullptr, 1, st);
+            // the FFN adjoint needs n2 = norm_2(x1) only through its stored outputs (y1, gp): no recompute
+            launch_rms_bwd_t<S>(gp<S>(x1s[l]), w.n2w, gp<S>(gn), gp<S>(gx), n_nodes, gp<S>(gx1), st);   // g_x1
             // Edgewise adjoint
-            launch_rms_fwd(xs[l].f(), w.n1w, w.n1b, csd, n_nodes, nbuf.f(), st);       // recompute n1
-            for (const Chunk& c : chunks) edge_bwd_chunk(w, nbuf.f(), c, l, gx1.f(), gn.f(), st);
-            timed(P_SRC_REDUCE, n_edges * 4612.0 + n_nodes * 9216.0, st, [&] {
-                launch_source_reduce(Gbuf.f(), sptr.i(), sedge.i(), n_nodes, gn.f(), st); });
-            save_dbg("l" + std::to_string(l) + ".g_n1", gn.p, (size_t)n_nodes * 9 * C, st);
-            launch_rms_bwd(xs[l].f(), w.n1w, gn.f(), gx1.f(), n_nodes, gx.f(), st);    // g_x_l
-            save_dbg("l" + std::to_string(l) + ".g_x", gx.p, (size_t)n_nodes * 9 * C, st);
+            launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);         // recompute n1
+            for (const Chunk& c : chunks) edge_bwd_chunk<S>(w, gp<S>(nbuf), c, l, gp<S>(gx1), gp<S>(gn), st);
+            timed(P_SRC_REDUCE, planes<S>() * (n_edges * 4612.0 + n_nodes * 9216.0), st, [&] {
+                for (int k = 0; k < planes<S>(); ++k)
+                    launch_source_reduce(plane(gp<S>(Gbuf), k), sptr.i(), sedge.i(), n_nodes, plane(gp<S>(gn), k), st); });
+            save_dbg("l" + std::to_string(l) + ".g_n1", gn.v.p, (size_t)n_nodes * 9 * C, st);
+            launch_rms_bwd_t<S>(gp<S>(xs[l]), w.n1w, gp<S>(gn), gp<S>(gx1), n_nodes, gp<S>(gx), st);    // g_x_l
+            save_dbg("l" + std::to_string(l) + ".g_x", gx.v.p, (size_t)n_nodes * 9 * C, st);
         }
         // edge-degree embedding adjoint
         for (const Chunk& c : chunks) {
-            radial_fwd(ed_rad, c, st);
-            launch_rotate_back_bwd(1, wRAD.f(), nullptr, nullptr, tgt.i(), wig.f(), env.f(),
-                                   1.0f / cfg.edge_degree_rescale, c.e0, c.n_e, gx.f(), wRAD.f(), nullptr, nullptr,
-                                   g_env.f(), g_wig.f(), st);
-            radial_bwd(ed_rad, c, st);
+            const EB<S> b = bufs_for<S>(-1, c);
+            radial_fwd<S>(ed_rad, c, b, st);
+            launch_rotate_back_bwd_t<S>(1, b.rad, gnull<S>(), gnull<S>(), tgt.i(), gp<S>(wig), gp<S>(env),
+                                        1.0f / cfg.edge_degree_rescale, c.e0, c.n_e, gp<S>(gx), b.rad, gnull<S>(),
+                                        gnull<S>(), gp<S>(g_env), gp<S>(g_wig), st);
+            radial_bwd<S>(ed_rad, c, b, st);
         }
-        save_dbg("g_gauss", g_gauss.p, (size_t)n_edges * NB, st);
-        save_dbg("g_env", g_env.p, (size_t)n_edges, st);
-        save_dbg("g_wig", g_wig.p, (size_t)n_edges * WIG, st);
-        launch_geometry_bwd(vec.f(), dist.f(), wig.f(), gauss.f(), g_gauss.f(), g_env.f(), g_wig.f(), (int)n_edges,
-                            cfg.cutoff, g_vec.f(), st);
-        save_dbg("g_vec", g_vec.p, (size_t)n_edges * 3, st);
-        launch_force_reduce(g_vec.f(), row_ptr.i(), sptr.i(), sedge.i(), n_nodes, forces_dev, st);
+        save_dbg("g_gauss", g_gauss.v.p, (size_t)n_edges * NB, st);
+        save_dbg("g_env", g_env.v.p, (size_t)n_edges, st);
+        save_dbg("g_wig", g_wig.v.p, (size_t)n_edges * WIG, st);
+        launch_geometry_bwd_t<S>(gp<S>(vec), gp<S>(dist), gp<S>(wig), gp<S>(gauss), gp<S>(g_gauss), gp<S>(g_env),
+                                 gp<S>(g_wig), (int)n_edges, cfg.cutoff, gp<S>(g_vec), st);
+        save_dbg("g_vec", g_vec.v.p, (size_t)n_edges * 3, st);
+        for (int k = 0; k < planes<S>(); ++k)
+            launch_force_reduce(plane(gp<S>(g_vec), k), row_ptr.i(), sptr.i(), sedge.i(), n_nodes, plane(forces, k), st);
     }
 
     ~umab_engine() {
         tc_cache_destroy(tc_cache);
         for (auto& kv : weights) kv.second.buf.release();
         DevBuf* all[] = {&z1, &pos_own, &zt, &deg, &thr, &row_ptr, &src, &tgt, &odeg, &sptr, &cursor, &stmp, &sedge,
-                         &vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
-                         &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &node_e, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1,
-                         &wU2, &wH2, &e_dev, &f_dev};
+                         &node_e, &e_dev, &f_dev, &t_dev, &df_dev};
         for (DevBuf* b : all) b->release();
+        TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
+                        &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2};
+        for (TBuf* b : tall) b->release();
         for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore}) for (auto& b : *v) b.release();
         for (auto& kv : dbg) kv.second.first.release();
         if (h_pinned) cudaFreeHost(h_pinned);
@@ -656,6 +700,7 @@ int32_t umab_build_graph(umab_engine* e, const float* pos_dev, int32_t n_images,
     if (!e || !pos_dev) throw CudaError("null argument");
     DeviceGuard guard(e->cfg.device);
     e->build_graph(pos_dev, n_images, (cudaStream_t)stream);
+    e->plan_chunks<float>();
     UMAB_CATCH
 }
 
@@ -683,7 +728,7 @@ int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_t n_image
     UMAB_TRY
     if (!e || !pos_dev || !energy_dev) throw CudaError("null argument");
     DeviceGuard guard(e->cfg.device);
-    e->evaluate(pos_dev, n_images, energy_dev, forces_dev, (cudaStream_t)stream);
+    e->evaluate<float>(gpf(pos_dev), n_images, energy_dev, GP<float>{forces_dev}, (cudaStream_t)stream);
     UMAB_CATCH
 }
 
@@ -713,12 +758,28 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
     }
     memcpy(e->hp_pos, pos_host, nb);
     UMAB_CUDA(cudaMemcpyAsync(e->pos_own.p, e->hp_pos, nb, cudaMemcpyHostToDevice, st));
-    e->evaluate(e->pos_own.f(), n_images, e->e_dev.as<double>(), forces_host ? e->f_dev.f() : nullptr, st);
+    e->evaluate<float>(GP<float>{e->pos_own.f()}, n_images, e->e_dev.as<double>(),
+                       GP<float>{forces_host ? e->f_dev.f() : nullptr}, st);
     UMAB_CUDA(cudaMemcpyAsync(e->hp_e, e->e_dev.p, sizeof(double) * n_images, cudaMemcpyDeviceToHost, st));
     if (forces_host) UMAB_CUDA(cudaMemcpyAsync(e->hp_f, e->f_dev.p, nb, cudaMemcpyDeviceToHost, st));
     UMAB_CUDA(cudaStreamSynchronize(st));
     memcpy(energy_host, e->hp_e, sizeof(double) * n_images);
     if (forces_host) memcpy(forces_host, e->hp_f, nb);
+    UMAB_CATCH
+}
+
+int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const float* tangent_dev, int32_t n_images,
+                        double* energy_dev, float* forces_dev, float* dforces_dev, void* stream) {
+    UMAB_TRY
+    if (!e || !pos_dev || !tangent_dev || !dforces_dev) throw CudaError("null argument");
+    DeviceGuard guard(e->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!forces_dev) {
+        e->f_dev.ensure((size_t)n_images * e->n_atoms * 3 * sizeof(float));
+        forces_dev = e->f_dev.f();
+    }
+    e->evaluate<D1>(GP<D1>{const_cast<float*>(pos_dev), const_cast<float*>(tangent_dev)}, n_images, energy_dev,
+                    GP<D1>{forces_dev, dforces_dev}, st);
     UMAB_CATCH
 }
 

@@ -10,7 +10,7 @@
 // every target of a CTA reuses the tile.  Sources are visited in increasing index, so each CSR
 // row comes out sorted by source: the output is the canonical (target, source) order without a
 // sort.  Two passes (count, fill) around a prefix sum.
-#include "common.cuh"
+#include "kernels.cuh"
 
 namespace umab {
 

@@ -19,7 +19,7 @@ from .arch import UMAArch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -28,7 +28,7 @@ GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
 EXPORTS = (
     "umab_abi_version", "umab_last_error", "umab_create", "umab_destroy", "umab_set_weight",
     "umab_finalize_weights", "umab_set_system", "umab_build_graph", "umab_graph_counts",
-    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_gemm",
+    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
 )
 
@@ -75,6 +75,7 @@ def load_library(path: Optional[str] = None):
     lib.umab_graph_copy.argtypes = [vp, vp, vp, vp, vp]
     lib.umab_energy_forces.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.umab_energy_forces_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.umab_forces_jvp.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.umab_gemm.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.umab_debug_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -288,6 +289,24 @@ class UmabEngine:
                 step = self.images_per_call(forces)
             s = t
         return e, f
+
+    # ------------------------------------------------------------------ analytic Hessian columns
+    def forces_jvp(self, pos: torch.Tensor, tangent: torch.Tensor):
+        """pos, tangent [B, N, 3] float32 CUDA -> (F [B,N,3], dF [B,N,3]) with
+        dF = d(forces)/d(eps) at pos + eps * tangent  (= -H . tangent), computed by running the
+        forward and the hand-written backward on dual numbers (no finite differences)."""
+        assert pos.is_cuda and pos.dtype == torch.float32 and pos.dim() == 3 and pos.shape[1] == self.n_atoms
+        assert tangent.shape == pos.shape and tangent.dtype == torch.float32 and tangent.is_cuda
+        pos, tangent = pos.contiguous(), tangent.contiguous()
+        b = pos.shape[0]
+        f = torch.empty_like(pos)
+        df = torch.empty_like(pos)
+        step = max(1, self.images_per_call(True) // 2)          # dual tensors: twice the memory per image
+        for s in range(0, b, step):
+            t = min(b, s + step)
+            _check(self.lib, self.lib.umab_forces_jvp(self._h, pos[s:t].data_ptr(), tangent[s:t].data_ptr(), t - s, None,
+                                                      f[s:t].data_ptr(), df[s:t].data_ptr(), self._stream_ptr()))
+        return f, df
 
     def graph(self, pos: torch.Tensor):
         """Neighbour search only -> edge_index [2, E] int64 (row 0 source, row 1 target), CPU."""

@@ -130,6 +130,9 @@ template <> struct GP<float> {
     __host__ __device__ GP operator+(long long o) const { return GP{p + o}; }
     __host__ __device__ explicit operator bool() const { return p != nullptr; }
     __device__ __forceinline__ float4 ld4(long long i) const { return *reinterpret_cast<const float4*>(p + i); }
+    // read-only path: only for tensors the kernel never writes (not for in-place operands)
+    __device__ __forceinline__ float4 ldg4(long long i) const { return __ldg(reinterpret_cast<const float4*>(p + i)); }
+    __device__ __forceinline__ float ldg(long long i) const { return __ldg(p + i); }
     __device__ __forceinline__ void st4(long long i, float4 x) const { *reinterpret_cast<float4*>(p + i) = x; }
     __device__ __forceinline__ float ld(long long i) const { return p[i]; }
     __device__ __forceinline__ void st(long long i, float x) const { p[i] = x; }
@@ -142,6 +145,10 @@ template <> struct GP<D1> {
     __device__ __forceinline__ D4 ld4(long long i) const {
         return D4{*reinterpret_cast<const float4*>(v + i), *reinterpret_cast<const float4*>(d + i)};
     }
+    __device__ __forceinline__ D4 ldg4(long long i) const {
+        return D4{__ldg(reinterpret_cast<const float4*>(v + i)), __ldg(reinterpret_cast<const float4*>(d + i))};
+    }
+    __device__ __forceinline__ D1 ldg(long long i) const { return D1{__ldg(v + i), __ldg(d + i)}; }
     __device__ __forceinline__ void st4(long long i, D4 x) const {
         *reinterpret_cast<float4*>(v + i) = x.v;
         *reinterpret_cast<float4*>(d + i) = x.d;
@@ -149,6 +156,9 @@ template <> struct GP<D1> {
     __device__ __forceinline__ D1 ld(long long i) const { return D1{v[i], d[i]}; }
     __device__ __forceinline__ void st(long long i, D1 x) const { v[i] = x.v; d[i] = x.d; }
 };
+// occupancy hint: the float instantiations keep the register budgets of the hand-tuned float kernels
+template <class S> constexpr int min_blocks(int for_float) { return std::is_same<S, float>::value ? for_float : 1; }
+
 inline GP<float> gpf(const float* p) { return GP<float>{const_cast<float*>(p)}; }
 
 }  // namespace umab

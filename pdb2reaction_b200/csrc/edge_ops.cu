@@ -27,7 +27,7 @@ __device__ __forceinline__ WigReg<S> load_wig(GP<S> wig, long long e) {
     S t[36];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        V v = wig.ld4(e * WIG + 4 * i);
+        V v = wig.ldg4(e * WIG + 4 * i);
         if constexpr (std::is_same<S, float>::value) {
             t[i * 4 + 0] = v.x; t[i * 4 + 1] = v.y; t[i * 4 + 2] = v.z; t[i * 4 + 3] = v.w;
         } else {
@@ -141,7 +141,7 @@ __device__ __forceinline__ void wig_grad_commit(S (&acc)[34], S scale, GP<S> g_w
 
 // ------------------------------------------------------------------ gather + rotate + radial scale
 template <class S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, min_blocks<S>(3))
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
                            long long e0, int n_e, GP<S> A0, GP<S> A1, GP<S> A2) {
     using V = typename VecOf<S>::type;
@@ -158,11 +158,11 @@ gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __re
         const long long xp = (long long)node * (9 * C) + lane * 4;
         V xr[9], yl[9];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) xr[r] = x.ld4(xp + r * C);
+        for (int r = 0; r < 9; ++r) xr[r] = x.ldg4(xp + r * C);
         rot_fwd(w, xr, yl);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-            V rv = rad.ld4(rp + r_off(k) + half * C);
+            V rv = rad.ldg4(rp + r_off(k) + half * C);
             bufs[a_buf(k)].st4(a_off(k) + half * C + lane * 4, vmul(yl[to_m(k)], rv));
         }
     }
@@ -200,13 +200,13 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
             V xr[9], yl[9], gml[9];
             V g_rad_v[6];      // radial groups 0,1,2 (m=0 rows), 3,4 (m=1: l=1,2), 5 (m=2)
 #pragma unroll
-            for (int r = 0; r < 9; ++r) xr[r] = x.ld4(xp + r * C);
+            for (int r = 0; r < 9; ++r) xr[r] = x.ldg4(xp + r * C);
             rot_fwd(w, xr, yl);
 #pragma unroll
             for (int q = 0; q < 6; ++q) g_rad_v[q] = vzero<V>();
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                V ga = gbufs[a_buf(k)].ld4(a_off(k) + half * C + lane * 4);
+                V ga = gbufs[a_buf(k)].ldg4(a_off(k) + half * C + lane * 4);
                 V rv = rad.ld4(rp + r_off(k) + half * C);
                 const int grp_id = k < 3 ? k : (k == 3 || k == 5 ? 3 : (k == 4 || k == 6 ? 4 : 5));
                 g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(k)]));
@@ -259,7 +259,7 @@ source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, 
 
 // ------------------------------------------------------------------ combine + gate (between the convs)
 template <class S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, min_blocks<S>(4))
 combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B1, GP<S> B2) {
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
@@ -292,7 +292,7 @@ combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B
 
 // gY* may alias Y* (gB* are read-only)
 template <class S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, min_blocks<S>(3))
 combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, GP<S> gY0, GP<S> gY1,
                         GP<S> gY2) {
     using V = typename VecOf<S>::type;
@@ -377,7 +377,7 @@ __device__ __forceinline__ void load_zl(GP<S> Z0, GP<S> Z1, GP<S> Z2, long long 
 }
 
 template <int MODE, class S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ row_ptr, GP<S> wig, GP<S> env,
                           float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out) {   // base may alias out
     using V = typename VecOf<S>::type;
@@ -393,7 +393,7 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
         V zl[9], y[9];
         load_zl<MODE, S, V>(Z0, Z1, Z2, e - e0, lane, zl);
         rot_bwd(w, zl, y);
-        const S s = env.ld(e) * scale;
+        const S s = env.ldg(e) * scale;
 #pragma unroll
         for (int r = 0; r < 9; ++r) vfma(acc[r], s, y[r]);
     }
@@ -409,7 +409,7 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
 
 // adjoint, one warp per edge.  gZ* may alias Z*.
 template <int MODE, class S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
                        long long e0, int n_e, GP<S> g_out, GP<S> gZ0, GP<S> gZ1, GP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
     using V = typename VecOf<S>::type;
@@ -422,8 +422,8 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
     load_zl<MODE, S, V>(Z0, Z1, Z2, el, lane, zl);
     const long long gp = (long long)tgt[e] * (9 * C) + lane * 4;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) g[r] = g_out.ld4(gp + r * C);
-    const S s = env.ld(e) * scale;
+    for (int r = 0; r < 9; ++r) g[r] = g_out.ldg4(gp + r * C);
+    const S s = env.ldg(e) * scale;
     // d/denv
     rot_bwd(w, zl, t);
     S part = cst<S>(0.f);

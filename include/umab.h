@@ -55,7 +55,7 @@ typedef struct umab_config {
     int64_t workspace_bytes;    /* per-chunk edge workspace budget; 0 = default */
     int64_t store_bytes;        /* HBM budget for keeping the conv outputs of all layers for the backward
                                    (16.4 KB per edge and layer) instead of recomputing them: 0 = auto
-                                   (55 % of the device memory), -1 = never (always recompute) */
+                                   (45 % of the device memory), -1 = never (always recompute) */
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */

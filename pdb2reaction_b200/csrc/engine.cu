@@ -350,7 +350,7 @@ struct umab_engine {
     }
 
     template <class S> void plan_chunks() {
-        long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (32LL << 30);
+        long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (24LL << 30);
         long long cap = std::max<long long>(budget / (long long)(EDGE_WS_FLOATS * 4 * planes<S>()), 1024);
         chunks.clear();
         int node0 = 0;
@@ -475,7 +475,7 @@ struct umab_engine {
             if (cfg.store_bytes == 0) {
                 size_t fr = 0, tot = 0;
                 UMAB_CUDA(cudaMemGetInfo(&fr, &tot));
-                budget = 0.55 * (double)tot;
+                budget = 0.45 * (double)tot;
             }
             store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
             if (store_mode) {

@@ -12,13 +12,13 @@
 // so no extra HBM pass exists.
 //
 // Persistent kernel: one CTA per SM loops over 128 x BN output tiles (N fastest, so concurrent CTAs
-// share an A tile through L2); 448 threads:
-//   warps 0-7   A producers: coalesced LDG.128 of the fp32 tile (2 rows x 256 B per warp instruction, one
+// share an A tile through L2); 704 threads:
+//   warps 0-15  A producers: coalesced LDG.128 of the fp32 tile (2 rows x 256 B per warp instruction, one
 //               k block ahead, across tile boundaries), split, st.shared swizzled (8 B per plane),
 //               fence.proxy.async, mbarrier arrive
-//   warp 8      TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
-//   warp 9      single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
-//   warps 10-13 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
+//   warp 16     TMEM allocator + TMA producer of the W_hi / W_lo tiles (cp.async.bulk.tensor)
+//   warp 17     single-thread tcgen05.mma issuer (3 MMAs per 16-wide k step), tcgen05.commit
+//   warps 18-21 epilogue: tcgen05.ld (lane quadrant warp%4) -> smem transpose -> (+bias,+C) ->
 //               fully coalesced STG.128; overlaps the next tile's main loop through the
 //               double-buffered TMEM accumulator (2 x tmem_cols columns)
 // smem ring of S stages {A_hi, A_lo, W_hi, W_lo}; mbarriers full_a / full_b / empty per stage and
@@ -38,8 +38,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;                 // bf16 elements per k block = one 128 B swizzle row
-constexpr int TC_THREADS = 448;
-constexpr int PRODUCER_THREADS = 256;
+constexpr int PRODUCER_WARPS = 16;
+constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
+constexpr int ROWS_PER_WARP = 128 / PRODUCER_WARPS;        // tile rows owned by one producer warp
+constexpr int LD_PER_KB = ROWS_PER_WARP / 2;               // LDG.128 per thread and k block (2 rows each)
+constexpr int TC_THREADS = PRODUCER_THREADS + 2 * 32 + 4 * 32;   // + TMA warp + MMA warp + 4 epilogue warps
 constexpr int EPI_PITCH = 36;                       // floats per staged row (16 B aligned, conflict-free)
 constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_PITCH * 4;   // per-warp transpose buffers of the epilogue
 constexpr int A_TILE_BYTES = BM * 128; // one bf16 plane of the A tile
@@ -168,12 +171,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int num_tiles = ntn * ((p.M + BM - 1) / BM);
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == 9 && lane == 0) {
+    if (warp == PRODUCER_WARPS + 1 && lane == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_a(s), PRODUCER_THREADS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == PRODUCER_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -182,37 +185,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 8) {
+    if (warp < PRODUCER_WARPS) {
         // ===================== A producers: fp32 -> bf16 hi/lo, swizzled K-major tiles.
-        // Coalesced mapping: a warp owns 16 tile rows; each LDG.128 instruction covers 2 full rows of
-        // the k block (16 lanes x 16 B = 256 B per row -> 4 cache lines per instruction), 8
-        // instructions per k block.  A lane converts its 4 floats and stores 8 B of the hi and of
-        // the lo plane (2 smem wavefronts per 256 B instruction = the minimum).
-        // One flat loop over (tile, k block) so the prefetch runs across tile boundaries.
+        // Coalesced mapping: a warp owns ROWS_PER_WARP tile rows; each LDG.128 instruction covers 2 full
+        // rows of the k block (16 lanes x 16 B = 256 B per row -> 4 cache lines per instruction).  A lane
+        // converts its 4 floats and stores 8 B of the hi and of the lo plane (2 smem wavefronts per
+        // 256 B instruction = the minimum).  One flat loop over (tile, k block) with the loads of the
+        // next TWO k blocks in flight, so the prefetch runs across tile boundaries.
         const int l16 = lane & 15;
-        const int rbase = warp * 16 + (lane >> 4);      // + 2*i
+        const int rbase = warp * ROWS_PER_WARP + (lane >> 4);      // + 2*i
         const int total = my_tiles * nkb;
-        float4 v[8], nx[8];
+        float4 v[LD_PER_KB], n1[LD_PER_KB], n2[LD_PER_KB];
         auto load_iter = [&](int g, float4* dst) {
             const int lt = g / nkb, kb = g - lt * nkb;
             const int tile = (int)blockIdx.x + lt * (int)gridDim.x;
             const long long mb = (long long)(tile / ntn) * BM;
             const float* src = p.A + (long long)kb * BK + l16 * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < LD_PER_KB; ++i) {
                 const long long m = mb + rbase + 2 * i;
                 dst[i] = (g < total && m < p.M) ? __ldg(reinterpret_cast<const float4*>(src + m * p.lda)) : f4zero();
             }
         };
         load_iter(0, v);
+        load_iter(1, n1);
         for (int g = 0; g < total; ++g) {
             const int s = g % S;
             const uint32_t ph = (uint32_t)(g / S) & 1u;
-            load_iter(g + 1, nx);
+            load_iter(g + 2, n2);
             mbar_wait(empty(s), ph ^ 1u);
             const uint32_t ah = a_hi(s), al = a_lo(s);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < LD_PER_KB; ++i) {
                 const int row = rbase + 2 * i;
                 const float4 x = v[i];
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
@@ -230,9 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(full_a(s));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = nx[i];
+            for (int i = 0; i < LD_PER_KB; ++i) { v[i] = n1[i]; n1[i] = n2[i]; }
         }
-    } else if (warp == 8) {
+    } else if (warp == PRODUCER_WARPS) {
         // ===================== TMA producer of the weight planes
         if (lane == 0) {
             int g = 0;
@@ -249,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == PRODUCER_WARPS + 1) {
         // ===================== MMA issuer (double-buffered TMEM accumulators)
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
@@ -281,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue warps 10-13: TMEM -> regs -> smem transpose -> coalesced STG
+        // ===================== epilogue warps (the last four; lane quadrant = warp % 4): TMEM -> regs -> smem transpose -> coalesced STG
         const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
         const uint32_t stg = epi_base + (uint32_t)q * (32u * EPI_PITCH * 4u);
         float* stg_ptr = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)));
@@ -326,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == PRODUCER_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
     }
 }

@@ -210,7 +210,7 @@ class UmabEngine:
         zz = np.ascontiguousarray(np.asarray(list(z), dtype=np.int32))
         _check(self.lib, self.lib.umab_set_system(self._h, zz.ctypes.data, int(zz.size)))
         self._store_budget = (-1 if store_bytes < 0 else store_bytes if store_bytes > 0 else
-                              0.55 * torch.cuda.get_device_properties(self.device).total_memory)
+                              0.45 * torch.cuda.get_device_properties(self.device).total_memory)
         self._edges_per_atom = 85.0          # refined from the measured graphs
         self.last_call_edges = 0             # edges summed over the sub-batches of the last public call
 

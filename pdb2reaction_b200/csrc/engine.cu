@@ -167,7 +167,6 @@ struct umab_engine {
     long long n_edges = 0;
     int zt_img = -1;
     DevBuf pos_own, zt, deg, thr, row_ptr, src, tgt, odeg, sptr, cursor, stmp, sedge;
-    std::vector<int> h_row_ptr;
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<Chunk> chunks;
     // geometry

@@ -99,10 +99,18 @@ UMAB_API int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const flo
                                  double* energy_dev, float* forces_dev, float* dforces_dev, void* stream);
 
 /* Standalone GEMM  C[M,N] = A[M,K] . W[N,K]^T (+bias), device pointers, for kernel unit tests
- * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3, 2 same with the bf16
- * weight planes cached by pointer (timing loops only). */
+ * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3 (activation split in the kernel),
+ * 2 same with the bf16 weight planes cached by pointer (timing loops only), 3 / 4 TMA-fed tensor-core
+ * bf16x3 kernel (activation pre-split into bf16 hi/lo planes, as the pipeline's producing kernels write
+ * it) with a 64 / 32 wide k block. */
 UMAB_API int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const float* bias_dev, float* c_dev,
                   int64_t m, int32_t n, int32_t k, void* stream);
+
+/* Kernel-only timing of one GEMM shape: `iters` back-to-back launches between two CUDA events on
+ * `stream` after one warm-up launch (weight planes, tensor maps and the activation split are prepared
+ * outside the timed region).  Modes as umab_gemm.  ms_per_iter: host pointer. */
+UMAB_API int32_t umab_gemm_bench(int32_t mode, const float* a_dev, const float* w_dev, float* c_dev, int64_t m, int32_t n,
+                        int32_t k, int32_t iters, double* ms_per_iter, void* stream);
 
 /* Debug access (config.debug = 1): device pointer + element count of a named intermediate of
  * the last umab_energy_forces call.  The pointer stays valid until the next call. */

@@ -260,17 +260,21 @@ def gather_rotate_scale(x, src, tgt, wig, rad):
     return a0, a1, a2, msg
 
 
-def so2_combine(ym, half):
-    """ym [E,2,2*half] -> (o_r, o_i) each [E, half]."""
-    yr, yi = ym[..., :half], ym[..., half:]
-    return yr[:, 0] - yi[:, 1], yr[:, 1] + yi[:, 0]
+def so2_complex_weight(w):
+    """SO(2) m>0 weight W [2*ho, i] (rows: real | imaginary outputs) -> Wc [2*ho, 2*i] = [[W_r, -W_i], [W_i, W_r]].
+
+    fairchem's SO2_m_Conv applies W to the +m and the -m rows separately and then combines
+    (o_r = y_r(+) - y_i(-), o_i = y_r(-) + y_i(+)).  Folding the combination into the weight gives the same
+    FLOPs in ONE contraction  [x(+m) | x(-m)] @ Wc^T = [o_r | o_i]  and halves the conv output the kernels have to
+    write and re-read (this is what the CUDA pipeline does; engine.prepare_engine_weights builds the same Wc)."""
+    ho = w.shape[0] // 2
+    wr, wi = w[:ho], w[ho:]
+    return torch.cat([torch.cat([wr, -wi], 1), torch.cat([wi, wr], 1)], 0)
 
 
-def so2_uncombine(g_r, g_i):
-    """adjoint of so2_combine -> g_ym [E,2,2*half]."""
-    row0 = torch.cat([g_r, g_i], -1)        # yr[0] <- g_r ; yi[0] <- g_i
-    row1 = torch.cat([g_i, -g_r], -1)       # yr[1] <- g_i ; yi[1] <- -g_r
-    return torch.stack([row0, row1], 1)
+def so2_split(ym, half):
+    """ym [E, 2*half] = [o_r | o_i] -> (o_r, o_i)."""
+    return ym[:, :half], ym[:, half:]
 
 
 def combine_gate_fwd(y0, y1, y2, h):
@@ -279,9 +283,9 @@ def combine_gate_fwd(y0, y1, y2, h):
     g = torch.sigmoid(y0[:, : 2 * h]).reshape(e, 2, h)
     t = y0[:, 2 * h:].reshape(e, 3, h)
     b0 = torch.stack([silu(t[:, 0]), t[:, 1] * g[:, 0], t[:, 2] * g[:, 1]], 1)
-    o_r, o_i = so2_combine(y1, 2 * h)
+    o_r, o_i = so2_split(y1, 2 * h)
     b1 = torch.stack([o_r.reshape(e, 2, h) * g, o_i.reshape(e, 2, h) * g], 1)
-    p_r, p_i = so2_combine(y2, h)
+    p_r, p_i = so2_split(y2, h)
     b2 = torch.stack([p_r * g[:, 1], p_i * g[:, 1]], 1).reshape(e, 2, 1, h)
     return b0, b1, b2
 
@@ -290,25 +294,25 @@ def combine_gate_bwd(y0, y1, y2, h, g_b0, g_b1, g_b2):
     e = y0.shape[0]
     sg = torch.sigmoid(y0[:, : 2 * h]).reshape(e, 2, h)
     t = y0[:, 2 * h:].reshape(e, 3, h)
-    o_r, o_i = so2_combine(y1, 2 * h)
+    o_r, o_i = so2_split(y1, 2 * h)
     o_r, o_i = o_r.reshape(e, 2, h), o_i.reshape(e, 2, h)
-    p_r, p_i = so2_combine(y2, h)
+    p_r, p_i = so2_split(y2, h)
     g_gate = torch.zeros_like(sg)
     g_gate[:, 0] = g_b0[:, 1] * t[:, 1] + g_b1[:, 0, 0] * o_r[:, 0] + g_b1[:, 1, 0] * o_i[:, 0]
     g_gate[:, 1] = (g_b0[:, 2] * t[:, 2] + g_b1[:, 0, 1] * o_r[:, 1] + g_b1[:, 1, 1] * o_i[:, 1]
                     + g_b2[:, 0, 0] * p_r + g_b2[:, 1, 0] * p_i)
     g_t = torch.stack([g_b0[:, 0] * dsilu(t[:, 0]), g_b0[:, 1] * sg[:, 0], g_b0[:, 2] * sg[:, 1]], 1)
     g_y0 = torch.cat([(g_gate * sg * (1 - sg)).reshape(e, 2 * h), g_t.reshape(e, 3 * h)], 1)
-    g_y1 = so2_uncombine((g_b1[:, 0] * sg).reshape(e, 2 * h), (g_b1[:, 1] * sg).reshape(e, 2 * h))
-    g_y2 = so2_uncombine(g_b2[:, 0, 0] * sg[:, 1], g_b2[:, 1, 0] * sg[:, 1])
+    g_y1 = torch.cat([(g_b1[:, 0] * sg).reshape(e, 2 * h), (g_b1[:, 1] * sg).reshape(e, 2 * h)], 1)
+    g_y2 = torch.cat([g_b2[:, 0, 0] * sg[:, 1], g_b2[:, 1, 0] * sg[:, 1]], 1)
     return g_y0, g_y1, g_y2
 
 
 def z_rows(z0, z1, z2, c):
     """conv2 outputs -> message [E,9,C] in m-primary order."""
     e = z0.shape[0]
-    o_r, o_i = so2_combine(z1, 2 * c)
-    p_r, p_i = so2_combine(z2, c)
+    o_r, o_i = so2_split(z1, 2 * c)
+    p_r, p_i = so2_split(z2, c)
     return torch.cat([z0.reshape(e, 3, c), o_r.reshape(e, 2, c), o_i.reshape(e, 2, c),
                       p_r.reshape(e, 1, c), p_i.reshape(e, 1, c)], 1)
 
@@ -316,8 +320,8 @@ def z_rows(z0, z1, z2, c):
 def z_rows_bwd(g_zm, c):
     e = g_zm.shape[0]
     g_z0 = g_zm[:, 0:3].reshape(e, 3 * c)
-    g_z1 = so2_uncombine(g_zm[:, 3:5].reshape(e, 2 * c), g_zm[:, 5:7].reshape(e, 2 * c))
-    g_z2 = so2_uncombine(g_zm[:, 7].reshape(e, c), g_zm[:, 8].reshape(e, c))
+    g_z1 = torch.cat([g_zm[:, 3:5].reshape(e, 2 * c), g_zm[:, 5:7].reshape(e, 2 * c)], 1)
+    g_z2 = torch.cat([g_zm[:, 7].reshape(e, c), g_zm[:, 8].reshape(e, c)], 1)
     return g_z0, g_z1, g_z2
 
 
@@ -348,12 +352,12 @@ def edgewise_fwd(w, p, x, geo, src, tgt, zsrc, ztgt, c, h):
     a0, a1, a2, _ = gather_rotate_scale(x, src, tgt, geo["wig"], rad)
     e = src.shape[0]
     y0 = a0.reshape(e, -1) @ w[p + ".edge.conv1.fc_m0.weight"].T + w[p + ".edge.conv1.fc_m0.bias"]
-    y1 = a1.reshape(e, 2, -1) @ w[p + ".edge.conv1.fc_m1.weight"].T
-    y2 = a2.reshape(e, 2, -1) @ w[p + ".edge.conv1.fc_m2.weight"].T
+    y1 = a1.reshape(e, -1) @ so2_complex_weight(w[p + ".edge.conv1.fc_m1.weight"]).T      # [E, 4H] = [o_r | o_i]
+    y2 = a2.reshape(e, -1) @ so2_complex_weight(w[p + ".edge.conv1.fc_m2.weight"]).T      # [E, 2H]
     b0, b1, b2 = combine_gate_fwd(y0, y1, y2, h)
     z0 = b0.reshape(e, -1) @ w[p + ".edge.conv2.fc_m0.weight"].T + w[p + ".edge.conv2.fc_m0.bias"]
-    z1 = b1.reshape(e, 2, -1) @ w[p + ".edge.conv2.fc_m1.weight"].T
-    z2 = b2.reshape(e, 2, -1) @ w[p + ".edge.conv2.fc_m2.weight"].T
+    z1 = b1.reshape(e, -1) @ so2_complex_weight(w[p + ".edge.conv2.fc_m1.weight"]).T
+    z2 = b2.reshape(e, -1) @ so2_complex_weight(w[p + ".edge.conv2.fc_m2.weight"]).T
     zm = z_rows(z0, z1, z2, c)
     out = rotate_back_reduce(zm, geo["wig"], geo["env"], tgt, x.shape[0])
     saved = dict(rad=rad, rs=rs, y0=y0, y1=y1, y2=y2, zm=zm)
@@ -366,12 +370,12 @@ def edgewise_bwd(w, p, x, geo, src, tgt, saved, g_out, c, h):
     g_zm, g_env, g_wig = rotate_back_bwd(saved["zm"], geo["wig"], geo["env"], tgt, g_out)
     g_z0, g_z1, g_z2 = z_rows_bwd(g_zm, c)
     g_b0 = (g_z0 @ w[p + ".edge.conv2.fc_m0.weight"]).reshape(e, 3, h)
-    g_b1 = (g_z1 @ w[p + ".edge.conv2.fc_m1.weight"]).reshape(e, 2, 2, h)
-    g_b2 = (g_z2 @ w[p + ".edge.conv2.fc_m2.weight"]).reshape(e, 2, 1, h)
+    g_b1 = (g_z1 @ so2_complex_weight(w[p + ".edge.conv2.fc_m1.weight"])).reshape(e, 2, 2, h)
+    g_b2 = (g_z2 @ so2_complex_weight(w[p + ".edge.conv2.fc_m2.weight"])).reshape(e, 2, 1, h)
     g_y0, g_y1, g_y2 = combine_gate_bwd(saved["y0"], saved["y1"], saved["y2"], h, g_b0, g_b1, g_b2)
     g_a0 = (g_y0 @ w[p + ".edge.conv1.fc_m0.weight"]).reshape(e, 3, 2 * c)
-    g_a1 = (g_y1 @ w[p + ".edge.conv1.fc_m1.weight"]).reshape(e, 2, 2, 2 * c)
-    g_a2 = (g_y2 @ w[p + ".edge.conv1.fc_m2.weight"]).reshape(e, 2, 1, 2 * c)
+    g_a1 = (g_y1 @ so2_complex_weight(w[p + ".edge.conv1.fc_m1.weight"])).reshape(e, 2, 2, 2 * c)
+    g_a2 = (g_y2 @ so2_complex_weight(w[p + ".edge.conv1.fc_m2.weight"])).reshape(e, 2, 1, 2 * c)
     # gather-rotate-scale adjoint
     rad = saved["rad"]
     dm = wig_full(geo["wig"])[:, TO_M, :]

@@ -1,5 +1,6 @@
 // Shared device/host helpers for the umab sm_100a kernels.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
@@ -62,9 +63,28 @@ __device__ __forceinline__ void f4fma(float4& acc, float s, float4 b) {
 __device__ __forceinline__ float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float f4hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand format of the bf16x3 tensor-core GEMMs
+__device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
+                        h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+    __nv_bfloat162 ha, hb;
+    ha.x = h0; ha.y = h1; hb.x = h2; hb.y = h3;
+    hi.x = *reinterpret_cast<uint32_t*>(&ha);
+    hi.y = *reinterpret_cast<uint32_t*>(&hb);
+    lo.x = pack_bf16(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
+    lo.y = pack_bf16(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+}
+
 // ---------------------------------------------------------------- GEMM (C = A W^T [+bias] [+C])
 struct GemmArgs {
     const float* A = nullptr; long long lda = 0; long long strideA = 0;
+    // pre-split activation operand (bf16 hi / lo planes, row pitch K) written by the producing kernel:
+    // when set, the tensor-core GEMM loads it by TMA and `A` is ignored
+    const __nv_bfloat16* A_hi = nullptr; const __nv_bfloat16* A_lo = nullptr;
     const float* W = nullptr; long long ldw = 0; long long strideW = 0;   // W is [N, K] row-major
     float* Cmat = nullptr;    long long ldc = 0; long long strideC = 0;
     const float* bias = nullptr;    // [N] or null

@@ -156,6 +156,39 @@ template <> struct GP<D1> {
     __device__ __forceinline__ D1 ld(long long i) const { return D1{v[i], d[i]}; }
     __device__ __forceinline__ void st(long long i, D1 x) const { v[i] = x.v; d[i] = x.d; }
 };
+// ------------------------------------------------------------------ A-operand outputs
+// An activation that is ONLY consumed as the A operand of a GEMM is written either as plain fp32 (exact SIMT
+// GEMMs, small systems) or directly in the operand format of the tensor-core GEMM: two bf16 planes hi / lo with
+// x ~= hi + lo (gemm_tc2.cu) -- the same 4 bytes per element, so the split costs no HBM traffic.
+// Element offsets are identical in both formats.
+template <class S> struct AP;
+template <> struct AP<float> {
+    float* p;
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    __host__ __device__ AP operator+(long long o) const {
+        return AP{p ? p + o : nullptr, hi ? hi + o : nullptr, lo ? lo + o : nullptr};
+    }
+    __device__ __forceinline__ void st4(long long i, float4 x) const {
+        if (hi) {
+            uint2 h, l;
+            split4(x, h, l);
+            *reinterpret_cast<uint2*>(hi + i) = h;
+            *reinterpret_cast<uint2*>(lo + i) = l;
+        } else {
+            *reinterpret_cast<float4*>(p + i) = x;
+        }
+    }
+};
+template <> struct AP<D1> {
+    AP<float> v, d;
+    __host__ __device__ AP operator+(long long o) const { return AP{v + o, d + o}; }
+    __device__ __forceinline__ void st4(long long i, D4 x) const {
+        v.st4(i, x.v);
+        d.st4(i, x.d);
+    }
+};
+
 // occupancy hint: the float instantiations keep the register budgets of the hand-tuned float kernels
 template <class S> constexpr int min_blocks(int for_float) { return std::is_same<S, float>::value ? for_float : 1; }
 

@@ -1,11 +1,13 @@
 // K6/K8/K10 and their adjoints: the memory-bound halves of the Edgewise block.
 //
 //   gather_rotate_scale   x[src], x[tgt] -> Wigner rotate (to m-primary) -> x radial weights
-//                         -> A0 [E,768] A1 [E,2,512] A2 [E,2,256]   (inputs of the SO(2) conv-1 GEMMs)
-//   combine_gate          conv-1 outputs Y0/Y1/Y2 -> complex combine + gate activation
-//                         -> B0 [E,384] B1 [E,2,256] B2 [E,2,128]   (inputs of the conv-2 GEMMs)
-//   rotate_back_reduce    conv-2 outputs Z0/Z1/Z2 -> combine -> x envelope -> rotate back
+//                         -> A0 [E,768] A1 [E,(+m|-m) 2x512] A2 [E,2x256]   (inputs of the SO(2) conv-1 GEMMs)
+//   combine_gate          conv-1 outputs Y0 [E,640] Y1 [E,(o_r|o_i) 2x256] Y2 [E,2x128] -> gate activation
+//                         -> B0 [E,384] B1 [E,2x256] B2 [E,2x128]   (inputs of the conv-2 GEMMs)
+//   rotate_back_reduce    conv-2 outputs Z0 [E,384] Z1 [E,2x256] Z2 [E,2x128] -> x envelope -> rotate back
 //                         -> segmented sum over the CSR row of each target (no atomics)
+// The (+m, -m) -> (real, imaginary) combination of SO2_m_Conv is folded into the m > 0 weights (complex block
+// form, engine.prepare_engine_weights), so the m > 0 GEMMs emit [o_r | o_i] directly: half the conv output.
 // and the matching backward kernels.  fairchem: Edgewise.forward / SO2_Convolution /
 // GateActivation / EdgeDegreeEmbedding, reached from the reference through predict_unit.predict
 // (pdb2reaction/uma_pysis.py:385).  All kernels: one warp per edge (or per target node for the
@@ -139,42 +141,99 @@ __device__ __forceinline__ void wig_grad_commit(S (&acc)[34], S scale, GP<S> g_w
     if (lane == 1) g_wig.st(o + 33, g_wig.ld(o + 33) + scale * t33);
 }
 
+// scalars [LO, LO+N) of the Wigner record of edge e (D1 = 0..8, D2 = 9..33)
+template <class S, int LO, int N>
+__device__ __forceinline__ void load_wig_part(GP<S> wig, long long e, S* out) {
+    using V = typename VecOf<S>::type;
+    constexpr int Q0 = LO / 4, Q1 = (LO + N + 3) / 4;
+#pragma unroll
+    for (int q = Q0; q < Q1; ++q) {
+        const V v = wig.ldg4(e * WIG + 4 * q);
+        S t[4];
+        if constexpr (std::is_same<S, float>::value) {
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        } else {
+            t[0] = D1{v.v.x, v.d.x}; t[1] = D1{v.v.y, v.d.y}; t[2] = D1{v.v.z, v.d.z}; t[3] = D1{v.v.w, v.d.w};
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int idx = 4 * q + jj - LO;
+            if (idx >= 0 && idx < N) out[idx] = t[jj];
+        }
+    }
+}
+// l-primary coefficient index -> m-primary row (inverse of to_m)
+__device__ __forceinline__ constexpr int from_l(int l) {
+    constexpr int t[9] = {0, 5, 1, 3, 8, 6, 2, 4, 7};
+    return t[l];
+}
+
 // ------------------------------------------------------------------ gather + rotate + radial scale
+// Processed one l block at a time (l = 0, then the 3x3, then the 5x5 Wigner block) so that only one block of
+// Wigner scalars and node rows is live: the kernel stays inside 80 registers (3 CTAs per SM) with the bf16
+// hi/lo operand stores.
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
-                           long long e0, int n_e, GP<S> A0, GP<S> A1, GP<S> A2) {
+                           long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long e = e0 + el;
-    const WigReg<S> w = load_wig<S>(wig, e);
     const long long rp = (long long)el * RAD1 + lane * 4;
-    const GP<S> bufs[3] = {A0 + (long long)el * 768, A1 + (long long)el * 1024, A2 + (long long)el * 512};
-#pragma unroll
+    const long long i0 = (long long)el * 768 + lane * 4, i1 = (long long)el * 1024 + lane * 4,
+                    i2 = (long long)el * 512 + lane * 4;
+#pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         const int node = half == 0 ? src[e] : tgt[e];
         const long long xp = (long long)node * (9 * C) + lane * 4;
-        V xr[9], yl[9];
+        // m-primary row k of the rotated message: times its radial weight, into the operand buffer of its m block
+        auto put = [&](int k, V y) {
+            const V o = vmul(y, rad.ldg4(rp + r_off(k) + half * C));
+            if (a_buf(k) == 0) A0.st4(i0 + a_off(k) + half * C, o);
+            else if (a_buf(k) == 1) A1.st4(i1 + a_off(k) + half * C, o);
+            else A2.st4(i2 + a_off(k) + half * C, o);
+        };
+        put(from_l(0), x.ldg4(xp));
+        {
+            S d[9];
+            load_wig_part<S, 0, 9>(wig, e, d);
+            V xr[3];
 #pragma unroll
-        for (int r = 0; r < 9; ++r) xr[r] = x.ldg4(xp + r * C);
-        rot_fwd(w, xr, yl);
+            for (int b = 0; b < 3; ++b) xr[b] = x.ldg4(xp + (1 + b) * C);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            V rv = rad.ldg4(rp + r_off(k) + half * C);
-            bufs[a_buf(k)].st4(a_off(k) + half * C + lane * 4, vmul(yl[to_m(k)], rv));
+            for (int a = 0; a < 3; ++a) {
+                V y = vzero<V>();
+#pragma unroll
+                for (int b = 0; b < 3; ++b) vfma(y, d[a * 3 + b], xr[b]);
+                put(from_l(1 + a), y);
+            }
+        }
+        {
+            S d[25];
+            load_wig_part<S, 9, 25>(wig, e, d);
+            V xr[5];
+#pragma unroll
+            for (int b = 0; b < 5; ++b) xr[b] = x.ldg4(xp + (4 + b) * C);
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                V y = vzero<V>();
+#pragma unroll
+                for (int b = 0; b < 5; ++b) vfma(y, d[a * 5 + b], xr[b]);
+                put(from_l(4 + a), y);
+            }
         }
     }
 }
 
 // adjoint: one warp per TARGET node of the chunk, looping over its CSR row.
-//   g_rad (may alias rad) [E,1536];  G[e] = dL/dx[src] contribution [9,128] (l-primary);
+//   g_rad [E,1536] (A operand of the radial adjoint GEMM; never aliases rad);  G[e] = dL/dx[src] contribution [9,128] (l-primary);
 //   g_x[i] = sum over the row of the target-half contributions;  g_wig[e] += ...
 template <class S>
 __global__ void __launch_bounds__(256)
 gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __restrict__ src, GP<S> wig, GP<S> rad,
-                         long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, GP<S> g_rad, GP<S> G,
+                         long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                          GP<S> g_x, GP<S> g_wig) {
     using V = typename VecOf<S>::type;
     const int nl = blockIdx.x * 8 + threadIdx.x / 32;
@@ -207,12 +266,11 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 V ga = gbufs[a_buf(k)].ldg4(a_off(k) + half * C + lane * 4);
-                V rv = rad.ld4(rp + r_off(k) + half * C);
+                V rv = rad.ldg4(rp + r_off(k) + half * C);
                 const int grp_id = k < 3 ? k : (k == 3 || k == 5 ? 3 : (k == 4 || k == 6 ? 4 : 5));
                 g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(k)]));
                 gml[to_m(k)] = vmul(ga, rv);
             }
-            // every read of this lane's rad[e] columns of this half is done: g_rad may alias rad
 #pragma unroll
             for (int q = 0; q < 3; ++q) g_rad.st4(rp + q * 256 + half * C, g_rad_v[q]);
             g_rad.st4(rp + 768 + half * C, g_rad_v[3]);
@@ -260,75 +318,70 @@ source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, 
 // ------------------------------------------------------------------ combine + gate (between the convs)
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(4))
-combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B1, GP<S> B2) {
+combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2) {
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long y0 = (long long)el * 640 + lane * 4;
-    const long long y1 = (long long)el * 1024 + lane * 4;
-    const long long y2 = (long long)el * 512 + lane * 4;
+    const long long y1 = (long long)el * 512 + lane * 4;
+    const long long y2 = (long long)el * 256 + lane * 4;
     V g[2];
 #pragma unroll
-    for (int l = 0; l < 2; ++l) g[l] = vsigmoid(Y0.ld4(y0 + l * 128));
+    for (int l = 0; l < 2; ++l) g[l] = vsigmoid(Y0.ldg4(y0 + l * 128));
     const long long b0 = (long long)el * 384 + lane * 4;
-    B0.st4(b0, vsilu(Y0.ld4(y0 + 256)));
-    B0.st4(b0 + 128, vmul(Y0.ld4(y0 + 384), g[0]));
-    B0.st4(b0 + 256, vmul(Y0.ld4(y0 + 512), g[1]));
+    B0.st4(b0, vsilu(Y0.ldg4(y0 + 256)));
+    B0.st4(b0 + 128, vmul(Y0.ldg4(y0 + 384), g[0]));
+    B0.st4(b0 + 256, vmul(Y0.ldg4(y0 + 512), g[1]));
     const long long b1 = (long long)el * 512 + lane * 4;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        V o_r = vsub(Y1.ld4(y1 + l * 128), Y1.ld4(y1 + 512 + 256 + l * 128));
-        V o_i = vadd(Y1.ld4(y1 + 512 + l * 128), Y1.ld4(y1 + 256 + l * 128));
-        B1.st4(b1 + l * 128, vmul(o_r, g[l]));
-        B1.st4(b1 + 256 + l * 128, vmul(o_i, g[l]));
+        B1.st4(b1 + l * 128, vmul(Y1.ldg4(y1 + l * 128), g[l]));                  // o_r
+        B1.st4(b1 + 256 + l * 128, vmul(Y1.ldg4(y1 + 256 + l * 128), g[l]));      // o_i
     }
     const long long b2 = (long long)el * 256 + lane * 4;
-    V p_r = vsub(Y2.ld4(y2), Y2.ld4(y2 + 256 + 128));
-    V p_i = vadd(Y2.ld4(y2 + 256), Y2.ld4(y2 + 128));
-    B2.st4(b2, vmul(p_r, g[1]));
-    B2.st4(b2 + 128, vmul(p_i, g[1]));
+    B2.st4(b2, vmul(Y2.ldg4(y2), g[1]));
+    B2.st4(b2 + 128, vmul(Y2.ldg4(y2 + 128), g[1]));
 }
 
-// gY* may alias Y* (gB* are read-only)
+// gY* (A operands of the conv-1 adjoint GEMMs) never alias Y*
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
-combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, GP<S> gY0, GP<S> gY1,
-                        GP<S> gY2) {
+combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0, AP<S> gY1,
+                        AP<S> gY2) {
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long y0 = (long long)el * 640 + lane * 4;
-    const long long y1 = (long long)el * 1024 + lane * 4;
-    const long long y2 = (long long)el * 512 + lane * 4;
+    const long long y1 = (long long)el * 512 + lane * 4;
+    const long long y2 = (long long)el * 256 + lane * 4;
     const long long gb0 = (long long)el * 384 + lane * 4;
     const long long gb1 = (long long)el * 512 + lane * 4;
     const long long gb2 = (long long)el * 256 + lane * 4;
     V sg[2], g_gate[2];
 #pragma unroll
-    for (int l = 0; l < 2; ++l) sg[l] = vsigmoid(Y0.ld4(y0 + l * 128));
-    V t0 = Y0.ld4(y0 + 256), t1 = Y0.ld4(y0 + 384), t2 = Y0.ld4(y0 + 512);
-    V gb00 = gB0.ld4(gb0), gb01 = gB0.ld4(gb0 + 128), gb02 = gB0.ld4(gb0 + 256);
+    for (int l = 0; l < 2; ++l) sg[l] = vsigmoid(Y0.ldg4(y0 + l * 128));
+    V t0 = Y0.ldg4(y0 + 256), t1 = Y0.ldg4(y0 + 384), t2 = Y0.ldg4(y0 + 512);
+    V gb00 = gB0.ldg4(gb0), gb01 = gB0.ldg4(gb0 + 128), gb02 = gB0.ldg4(gb0 + 256);
     g_gate[0] = vmul(gb01, t1);
     g_gate[1] = vmul(gb02, t2);
     V g_or[2], g_oi[2];
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        V o_r = vsub(Y1.ld4(y1 + l * 128), Y1.ld4(y1 + 512 + 256 + l * 128));
-        V o_i = vadd(Y1.ld4(y1 + 512 + l * 128), Y1.ld4(y1 + 256 + l * 128));
-        V br = gB1.ld4(gb1 + l * 128), bi = gB1.ld4(gb1 + 256 + l * 128);
+        V o_r = Y1.ldg4(y1 + l * 128);
+        V o_i = Y1.ldg4(y1 + 256 + l * 128);
+        V br = gB1.ldg4(gb1 + l * 128), bi = gB1.ldg4(gb1 + 256 + l * 128);
         g_gate[l] = vadd(g_gate[l], vadd(vmul(br, o_r), vmul(bi, o_i)));
         g_or[l] = vmul(br, sg[l]);
         g_oi[l] = vmul(bi, sg[l]);
     }
-    V p_r = vsub(Y2.ld4(y2), Y2.ld4(y2 + 256 + 128));
-    V p_i = vadd(Y2.ld4(y2 + 256), Y2.ld4(y2 + 128));
-    V b2r = gB2.ld4(gb2), b2i = gB2.ld4(gb2 + 128);
+    V p_r = Y2.ldg4(y2);
+    V p_i = Y2.ldg4(y2 + 128);
+    V b2r = gB2.ldg4(gb2), b2i = gB2.ldg4(gb2 + 128);
     g_gate[1] = vadd(g_gate[1], vadd(vmul(b2r, p_r), vmul(b2i, p_i)));
     V g_pr = vmul(b2r, sg[1]), g_pi = vmul(b2i, sg[1]);
 
-    // ---- all reads done; writes (possibly in place)
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
         // sigma'(y) = s (1 - s)
@@ -343,13 +396,9 @@ combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> 
     for (int l = 0; l < 2; ++l) {
         gY1.st4(y1 + l * 128, g_or[l]);
         gY1.st4(y1 + 256 + l * 128, g_oi[l]);
-        gY1.st4(y1 + 512 + l * 128, g_oi[l]);
-        gY1.st4(y1 + 512 + 256 + l * 128, vneg(g_or[l]));
     }
     gY2.st4(y2, g_pr);
     gY2.st4(y2 + 128, g_pi);
-    gY2.st4(y2 + 256, g_pi);
-    gY2.st4(y2 + 256 + 128, vneg(g_pr));
 }
 
 // ------------------------------------------------------------------ rotate back + segmented reduce
@@ -359,17 +408,17 @@ template <int MODE, class S, class V>
 __device__ __forceinline__ void load_zl(GP<S> Z0, GP<S> Z1, GP<S> Z2, long long el, int lane, V* zl) {
     const long long z0 = el * 384 + lane * 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) zl[to_m(k)] = Z0.ld4(z0 + k * 128);
+    for (int k = 0; k < 3; ++k) zl[to_m(k)] = Z0.ldg4(z0 + k * 128);
     if (MODE == 0) {
-        const long long z1 = el * 1024 + lane * 4;
-        const long long z2 = el * 512 + lane * 4;
+        const long long z1 = el * 512 + lane * 4;
+        const long long z2 = el * 256 + lane * 4;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            zl[to_m(3 + l)] = vsub(Z1.ld4(z1 + l * 128), Z1.ld4(z1 + 512 + 256 + l * 128));
-            zl[to_m(5 + l)] = vadd(Z1.ld4(z1 + 512 + l * 128), Z1.ld4(z1 + 256 + l * 128));
+            zl[to_m(3 + l)] = Z1.ldg4(z1 + l * 128);
+            zl[to_m(5 + l)] = Z1.ldg4(z1 + 256 + l * 128);
         }
-        zl[to_m(7)] = vsub(Z2.ld4(z2), Z2.ld4(z2 + 256 + 128));
-        zl[to_m(8)] = vadd(Z2.ld4(z2 + 256), Z2.ld4(z2 + 128));
+        zl[to_m(7)] = Z2.ldg4(z2);
+        zl[to_m(8)] = Z2.ldg4(z2 + 128);
     } else {
 #pragma unroll
         for (int k = 3; k < 9; ++k) zl[to_m(k)] = vzero<V>();
@@ -407,11 +456,11 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
     }
 }
 
-// adjoint, one warp per edge.  gZ* may alias Z*.
+// adjoint, one warp per edge.  gZ* (A operands of the conv-2 adjoint GEMMs) never alias Z*.
 template <int MODE, class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
-                       long long e0, int n_e, GP<S> g_out, GP<S> gZ0, GP<S> gZ1, GP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
+                       long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -443,21 +492,15 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
 #pragma unroll
     for (int k = 0; k < 3; ++k) gZ0.st4(o0 + k * 128, vscale(t[to_m(k)], s));
     if (MODE == 0) {
-        const long long o1 = (long long)el * 1024 + lane * 4;
-        const long long o2 = (long long)el * 512 + lane * 4;
+        const long long o1 = (long long)el * 512 + lane * 4;
+        const long long o2 = (long long)el * 256 + lane * 4;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            V g_or = vscale(t[to_m(3 + l)], s), g_oi = vscale(t[to_m(5 + l)], s);
-            gZ1.st4(o1 + l * 128, g_or);
-            gZ1.st4(o1 + 256 + l * 128, g_oi);
-            gZ1.st4(o1 + 512 + l * 128, g_oi);
-            gZ1.st4(o1 + 512 + 256 + l * 128, vneg(g_or));
+            gZ1.st4(o1 + l * 128, vscale(t[to_m(3 + l)], s));
+            gZ1.st4(o1 + 256 + l * 128, vscale(t[to_m(5 + l)], s));
         }
-        V g_pr = vscale(t[to_m(7)], s), g_pi = vscale(t[to_m(8)], s);
-        gZ2.st4(o2, g_pr);
-        gZ2.st4(o2 + 128, g_pi);
-        gZ2.st4(o2 + 256, g_pi);
-        gZ2.st4(o2 + 256 + 128, vneg(g_pr));
+        gZ2.st4(o2, vscale(t[to_m(7)], s));
+        gZ2.st4(o2 + 128, vscale(t[to_m(8)], s));
     }
 }
 
@@ -465,14 +508,14 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
 
 template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
-                                  GP<S> A0, GP<S> A1, GP<S> A2, cudaStream_t st) {
+                                  AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st) {
     if (n_e <= 0) return;
     gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<S> wig, GP<S> rad, long long e0,
-                                int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, GP<S> g_rad, GP<S> G,
+                                int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                                 GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
     gather_rotate_bwd_kernel<S><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
@@ -485,14 +528,14 @@ void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
-void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> B0, GP<S> B1, GP<S> B2, cudaStream_t st) {
+void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st) {
     if (n_e <= 0) return;
     combine_gate_fwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
-void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, GP<S> gY0,
-                               GP<S> gY1, GP<S> gY2, cudaStream_t st) {
+void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
+                               AP<S> gY1, AP<S> gY2, cudaStream_t st) {
     if (n_e <= 0) return;
     combine_gate_bwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
     UMAB_LAUNCH_CHECK();
@@ -511,7 +554,7 @@ void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const i
 }
 template <class S>
 void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* tgt, GP<S> wig, GP<S> env, float scale,
-                              long long e0, int n_e, GP<S> g_out, GP<S> gZ0, GP<S> gZ1, GP<S> gZ2, GP<S> g_env,
+                              long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env,
                               GP<S> g_wig, cudaStream_t st) {
     if (n_e <= 0) return;
     dim3 grid((n_e + 7) / 8);
@@ -523,17 +566,17 @@ void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int*
 }
 
 #define UMAB_INST(S)                                                                                                  \
-    template void launch_gather_rotate_scale_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, GP<S>,  \
-                                                  GP<S>, GP<S>, cudaStream_t);                                        \
+    template void launch_gather_rotate_scale_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, AP<S>,  \
+                                                  AP<S>, AP<S>, cudaStream_t);                                        \
     template void launch_gather_rotate_bwd_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, int,      \
-                                                GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);       \
-    template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, cudaStream_t);           \
-    template void launch_combine_gate_bwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>,     \
+                                                GP<S>, GP<S>, GP<S>, AP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);       \
+    template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, AP<S>, AP<S>, AP<S>, cudaStream_t);           \
+    template void launch_combine_gate_bwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, AP<S>, AP<S>, AP<S>,     \
                                                cudaStream_t);                                                         \
     template void launch_rotate_back_reduce_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long, \
                                                  int, int, GP<S>, GP<S>, cudaStream_t);                               \
     template void launch_rotate_back_bwd_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long,    \
-                                              int, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);
+                                              int, GP<S>, AP<S>, AP<S>, AP<S>, GP<S>, GP<S>, cudaStream_t);
 UMAB_INST(float)
 UMAB_INST(D1)
 #undef UMAB_INST

@@ -29,6 +29,13 @@ void tc_cache_destroy(TcPlaneCache* c);
 void tc_cache_clear(TcPlaneCache* c);
 void gemm_tc(const GemmArgs& a, cudaStream_t st, TcPlaneCache* cache);
 bool gemm_tc_supported(const GemmArgs& a);
+struct Tc2Cache;                                     // gemm_tc2.cu
+Tc2Cache* tc2_cache_create();
+void tc2_cache_destroy(Tc2Cache* c);
+void tc2_cache_clear(Tc2Cache* c);
+void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk);
+bool gemm_tc2_supported(const GemmArgs& a, int bk);
+void tc2_split(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 namespace {
 
@@ -80,10 +87,27 @@ template <> GP<D1> gp<D1>(const TBuf& b, long long off) { return GP<D1>{b.v.f() 
 template <class S> GP<S> gnull();
 template <> GP<float> gnull<float>() { return GP<float>{nullptr}; }
 template <> GP<D1> gnull<D1>() { return GP<D1>{nullptr, nullptr}; }
+template <class S> AP<S> anull();
+template <> AP<float> anull<float>() { return AP<float>{nullptr, nullptr, nullptr}; }
+template <> AP<D1> anull<D1>() { return AP<D1>{{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}; }
 template <class S> constexpr int planes() { return std::is_same<S, D1>::value ? 2 : 1; }
 inline float* plane(const GP<float>& g, int) { return g.p; }
 inline float* plane(const GP<D1>& g, int k) { return k == 0 ? g.v : g.d; }
-
+inline AP<float> plane(const AP<float>& a, int) { return a; }
+inline AP<float> plane(const AP<D1>& a, int k) { return k == 0 ? a.v : a.d; }
+// A-operand view of `cap_elems` elements at float offset `off` of a workspace buffer: fp32, or bf16 hi | lo planes
+inline AP<float> apf(float* base, long long off, long long cap_elems, bool split) {
+    if (!split) return AP<float>{base + off, nullptr, nullptr};
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base + off);
+    return AP<float>{nullptr, hi, hi + cap_elems};
+}
+template <class S> AP<S> ap(const TBuf& b, long long off, long long cap_elems, bool split);
+template <> AP<float> ap<float>(const TBuf& b, long long off, long long cap_elems, bool split) {
+    return apf(b.v.f(), off, cap_elems, split);
+}
+template <> AP<D1> ap<D1>(const TBuf& b, long long off, long long cap_elems, bool split) {
+    return AP<D1>{apf(b.v.f(), off, cap_elems, split), apf(b.d.f(), off, cap_elems, split)};
+}
 struct Weight { DevBuf buf; size_t numel = 0; };
 
 struct Chunk { int node0, n_nodes; long long e0; int n_e; };
@@ -141,7 +165,10 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-constexpr size_t EDGE_WS_FLOATS = 2304 + 2176 + 1152 + 1920 + 1536 + 4 * 128;   // 9600 per edge
+constexpr int YW = 640 + 512 + 256;      // conv-1 outputs per edge: m=0 | m=1 (o_r|o_i) | m=2 (p_r|p_i)
+constexpr int ZW = 384 + 512 + 256;      // conv-2 outputs per edge
+constexpr size_t EDGE_WS_FLOATS = 2304 + YW + 1152 + ZW + 1536 + 4 * 128;   // 8064 per edge
+constexpr size_t EDGE_WS_EXTRA_RECOMPUTE = YW + ZW;   // adjoint operands g_Y / g_Z when Y / Z live in the workspace
 
 }  // namespace
 }  // namespace umab
@@ -176,17 +203,19 @@ struct umab_engine {
     TBuf nbuf, abuf, gx, gx1, gn, ggp, p1, s1, p2, gp2, gs1, Gbuf;
     DevBuf node_e;
     // edge workspace
-    TBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2;
+    TBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2, wGY, wGZ;
     long long chunk_cap = 0;
     // store mode: conv-1 / conv-2 outputs of every layer are kept for the backward instead of being
     // recomputed (16.4 KB per edge and layer of HBM) when they fit `store_bytes`
     std::vector<TBuf> ystore, zstore;
     bool store_mode = false;
+    bool want_adjoint = false;                        // this evaluation runs the backward (forces requested)
     // host staging for umab_energy_forces_host
     DevBuf e_dev, f_dev, t_dev, df_dev;
     // debug
     std::map<std::string, std::pair<DevBuf, size_t>> dbg;
     TcPlaneCache* tc_cache = tc_cache_create();       // bf16 planes of this engine's weights
+    Tc2Cache* tc2_cache = tc2_cache_create();         // same for the TMA-fed GEMM (+ tensor maps of the workspace)
     // profiling + pinned host staging
     Prof prof;
     void* hp_pos = nullptr; void* hp_f = nullptr; void* hp_e = nullptr; size_t hp_cap = 0, hp_ecap = 0;
@@ -241,12 +270,13 @@ struct umab_engine {
             w.rad = radial(p + ".edge.conv1.rad", RAD1);
             w.c1m0 = W(p + ".edge.conv1.fc_m0.weight", 640 * 768); w.c1m0_t = W(p + ".edge.conv1.fc_m0.weight_t", 640 * 768);
             w.c1m0_b = W(p + ".edge.conv1.fc_m0.bias", 640);
-            w.c1m1 = W(p + ".edge.conv1.fc_m1.weight", 512 * 512); w.c1m1_t = W(p + ".edge.conv1.fc_m1.weight_t", 512 * 512);
-            w.c1m2 = W(p + ".edge.conv1.fc_m2.weight", 256 * 256); w.c1m2_t = W(p + ".edge.conv1.fc_m2.weight_t", 256 * 256);
+            // m > 0: complex block weights [[W_r, -W_i], [W_i, W_r]] (engine.prepare_engine_weights)
+            w.c1m1 = W(p + ".edge.conv1.fc_m1.weight", 512 * 1024); w.c1m1_t = W(p + ".edge.conv1.fc_m1.weight_t", 512 * 1024);
+            w.c1m2 = W(p + ".edge.conv1.fc_m2.weight", 256 * 512); w.c1m2_t = W(p + ".edge.conv1.fc_m2.weight_t", 256 * 512);
             w.c2m0 = W(p + ".edge.conv2.fc_m0.weight", 384 * 384); w.c2m0_t = W(p + ".edge.conv2.fc_m0.weight_t", 384 * 384);
             w.c2m0_b = W(p + ".edge.conv2.fc_m0.bias", 384);
-            w.c2m1 = W(p + ".edge.conv2.fc_m1.weight", 512 * 256); w.c2m1_t = W(p + ".edge.conv2.fc_m1.weight_t", 512 * 256);
-            w.c2m2 = W(p + ".edge.conv2.fc_m2.weight", 256 * 128); w.c2m2_t = W(p + ".edge.conv2.fc_m2.weight_t", 256 * 128);
+            w.c2m1 = W(p + ".edge.conv2.fc_m1.weight", 512 * 512); w.c2m1_t = W(p + ".edge.conv2.fc_m1.weight_t", 512 * 512);
+            w.c2m2 = W(p + ".edge.conv2.fc_m2.weight", 256 * 256); w.c2m2_t = W(p + ".edge.conv2.fc_m2.weight_t", 256 * 256);
             w.smlp = W(p + ".ffn.scalar_mlp.weight", 2 * H * C); w.smlp_t = W(p + ".ffn.scalar_mlp.weight_t", 2 * H * C);
             w.smlp_b = W(p + ".ffn.scalar_mlp.bias", 2 * H);
             w.so3_1 = W(p + ".ffn.so3_1.weight", 3 * H * C); w.so3_1_t = W(p + ".ffn.so3_1.weight_t", 3 * H * C);
@@ -265,7 +295,8 @@ struct umab_engine {
     bool use_tc() const { return cfg.gemm_mode == 1 || (cfg.gemm_mode == 2 && n_atoms >= 100); }
     void gemm(const GemmArgs& a, cudaStream_t st) {
         timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
-            if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
+            if (a.A_hi) gemm_tc2(a, st, tc2_cache, 0);
+            else if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
             else gemm_simt(a, st);
         }, /* algorithmic bytes: A and C once (+C again when accumulating), W once */
            4.0 * a.batch * ((double)a.M * a.K + (double)a.M * a.N * (a.accumulate ? 2 : 1)) + 4.0 * a.N * (double)a.K);
@@ -279,6 +310,20 @@ struct umab_engine {
             g.A = plane(A, k); g.lda = lda; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
             g.bias = k == 0 ? bias : nullptr;
             g.M = (int)M; g.N = N; g.K = K; g.accumulate = accumulate;
+            gemm(g, st);
+        }
+    }
+    // same with an A operand written by an elementwise kernel (fp32, or bf16 hi/lo planes for the TMA-fed GEMM)
+    template <class S>
+    void mm_ap(AP<S> A, const float* Wt, int N, int K, GP<S> Cm, long long ldc, long long M, const float* bias,
+               cudaStream_t st) {
+        if (M <= 0) return;
+        for (int k = 0; k < planes<S>(); ++k) {
+            const AP<float> a = plane(A, k);
+            GemmArgs g;
+            g.A = a.p; g.A_hi = a.hi; g.A_lo = a.lo; g.lda = K; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
+            g.bias = k == 0 ? bias : nullptr;
+            g.M = (int)M; g.N = N; g.K = K; g.accumulate = 0;
             gemm(g, st);
         }
     }
@@ -350,7 +395,9 @@ struct umab_engine {
 
     template <class S> void plan_chunks() {
         long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (24LL << 30);
-        long long cap = std::max<long long>(budget / (long long)(EDGE_WS_FLOATS * 4 * planes<S>()), 1024);
+        const bool extra = want_adjoint && !store_mode;
+        const size_t per_edge = EDGE_WS_FLOATS + (extra ? EDGE_WS_EXTRA_RECOMPUTE : 0);
+        long long cap = std::max<long long>(budget / (long long)(per_edge * 4 * planes<S>()), 1024);
         chunks.clear();
         int node0 = 0;
         long long biggest = 0;
@@ -366,29 +413,57 @@ struct umab_engine {
         }
         chunk_cap = std::max<long long>(biggest, 1);
         size_t f = sizeof(float) * (size_t)chunk_cap;
-        wA.ensure<S>(f * 2304); wY.ensure<S>(f * 2176); wB.ensure<S>(f * 1152); wZ.ensure<S>(f * 1920);
+        wA.ensure<S>(f * 2304); wY.ensure<S>(f * YW); wB.ensure<S>(f * 1152); wZ.ensure<S>(f * ZW);
         wRAD.ensure<S>(f * 1536);
         wU1.ensure<S>(f * 128); wH1.ensure<S>(f * 128); wU2.ensure<S>(f * 128); wH2.ensure<S>(f * 128);
+        if (extra) { wGY.ensure<S>(f * std::max(YW, 1536)); wGZ.ensure<S>(f * ZW); }
     }
 
     // ------------------------------------------------------------------ edge stages
-    template <class S> struct EB { GP<S> a0, a1, a2, b0, b1, b2, y0, y1, y2, z0, z1, z2, rad, u1, h1, u2, h2; };
+    // Buffers of one chunk.  A-operand activations (AP) are written by the elementwise kernels in the format of
+    // the GEMM that consumes them; the adjoint operands g_Y / g_Z / g_rad get buffers of their own (the format
+    // change rules out the in-place updates of an all-fp32 pipeline): the Y / Z workspace when Y / Z live in the
+    // per-layer stores, else wGY / wGZ.
+    template <class S> struct EB {
+        AP<S> a0, a1, a2, b0, b1, b2;            // conv-1 / conv-2 inputs
+        GP<S> ga0, ga1, ga2, gb0, gb1, gb2;      // their gradients (adjoint GEMM outputs, fp32, same memory)
+        GP<S> y0, y1, y2, z0, z1, z2;            // conv outputs
+        AP<S> gy0, gy1, gy2, gz0, gz1, gz2;      // gradients of the conv outputs (adjoint GEMM inputs)
+        AP<S> grad, ged;                         // g_rad [n_e,1536] / edge-degree g_rad [n_e,384]
+        GP<S> rad, u1, u2, h1f, h2f;             // radial MLP: fp32 tensors (h1f / h2f = fp32 views of h1 / h2)
+        AP<S> h1, h2, gu;                        // radial MLP: GEMM operands (gu = dL/du_2 in the h1 buffer)
+    };
     template <class S> EB<S> bufs_for(int layer, const Chunk& c) {
         EB<S> b;
         const long long cc = chunk_cap;
-        b.a0 = gp<S>(wA); b.a1 = gp<S>(wA, cc * 768); b.a2 = gp<S>(wA, cc * (768 + 1024));
-        b.b0 = gp<S>(wB); b.b1 = gp<S>(wB, cc * 384); b.b2 = gp<S>(wB, cc * (384 + 512));
-        if (store_mode && layer >= 0) {
+        const bool sp = use_tc();
+        b.a0 = ap<S>(wA, 0, cc * 768, sp); b.a1 = ap<S>(wA, cc * 768, cc * 1024, sp);
+        b.a2 = ap<S>(wA, cc * (768 + 1024), cc * 512, sp);
+        b.ga0 = gp<S>(wA); b.ga1 = gp<S>(wA, cc * 768); b.ga2 = gp<S>(wA, cc * (768 + 1024));
+        b.b0 = ap<S>(wB, 0, cc * 384, sp); b.b1 = ap<S>(wB, cc * 384, cc * 512, sp);
+        b.b2 = ap<S>(wB, cc * (384 + 512), cc * 256, sp);
+        b.gb0 = gp<S>(wB); b.gb1 = gp<S>(wB, cc * 384); b.gb2 = gp<S>(wB, cc * (384 + 512));
+        const bool stored = store_mode && layer >= 0;
+        if (stored) {
             const long long E = n_edges;
-            b.y0 = gp<S>(ystore[layer], c.e0 * 640); b.y1 = gp<S>(ystore[layer], E * 640 + c.e0 * 1024);
-            b.y2 = gp<S>(ystore[layer], E * 1664 + c.e0 * 512);
-            b.z0 = gp<S>(zstore[layer], c.e0 * 384); b.z1 = gp<S>(zstore[layer], E * 384 + c.e0 * 1024);
-            b.z2 = gp<S>(zstore[layer], E * 1408 + c.e0 * 512);
+            b.y0 = gp<S>(ystore[layer], c.e0 * 640); b.y1 = gp<S>(ystore[layer], E * 640 + c.e0 * 512);
+            b.y2 = gp<S>(ystore[layer], E * 1152 + c.e0 * 256);
+            b.z0 = gp<S>(zstore[layer], c.e0 * 384); b.z1 = gp<S>(zstore[layer], E * 384 + c.e0 * 512);
+            b.z2 = gp<S>(zstore[layer], E * 896 + c.e0 * 256);
         } else {
-            b.y0 = gp<S>(wY); b.y1 = gp<S>(wY, cc * 640); b.y2 = gp<S>(wY, cc * (640 + 1024));
-            b.z0 = gp<S>(wZ); b.z1 = gp<S>(wZ, cc * 384); b.z2 = gp<S>(wZ, cc * (384 + 1024));
+            b.y0 = gp<S>(wY); b.y1 = gp<S>(wY, cc * 640); b.y2 = gp<S>(wY, cc * (640 + 512));
+            b.z0 = gp<S>(wZ); b.z1 = gp<S>(wZ, cc * 384); b.z2 = gp<S>(wZ, cc * (384 + 512));
         }
-        b.rad = gp<S>(wRAD); b.u1 = gp<S>(wU1); b.h1 = gp<S>(wH1); b.u2 = gp<S>(wU2); b.h2 = gp<S>(wH2);
+        const TBuf& gyb = store_mode ? wY : wGY;
+        const TBuf& gzb = store_mode ? wZ : wGZ;
+        b.gy0 = ap<S>(gyb, 0, cc * 640, sp); b.gy1 = ap<S>(gyb, cc * 640, cc * 512, sp);
+        b.gy2 = ap<S>(gyb, cc * (640 + 512), cc * 256, sp);
+        b.gz0 = ap<S>(gzb, 0, cc * 384, sp); b.gz1 = ap<S>(gzb, cc * 384, cc * 512, sp);
+        b.gz2 = ap<S>(gzb, cc * (384 + 512), cc * 256, sp);
+        b.grad = ap<S>(gyb, 0, cc * 1536, sp);       // written after the conv-1 adjoint GEMMs have consumed g_Y
+        b.ged = ap<S>(gyb, 0, cc * 384, sp);
+        b.rad = gp<S>(wRAD); b.u1 = gp<S>(wU1); b.u2 = gp<S>(wU2); b.h1f = gp<S>(wH1); b.h2f = gp<S>(wH2);
+        b.h1 = ap<S>(wH1, 0, cc * 128, sp); b.h2 = ap<S>(wH2, 0, cc * 128, sp); b.gu = ap<S>(wH1, 0, cc * 128, sp);
         return b;
     }
 
@@ -396,17 +471,18 @@ struct umab_engine {
         const long long e0 = c.e0;
         mm<S>(gp<S>(gauss, e0 * NB), NB, r.w1g, 128, NB, b.u1, 128, c.n_e, nullptr, 0, st);
         launch_ln_silu_fwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st);
-        mm<S>(b.h1, 128, r.w2, 128, 128, b.u2, 128, c.n_e, r.b2, 0, st);
+        mm_ap<S>(b.h1, r.w2, 128, 128, b.u2, 128, c.n_e, r.b2, st);
         launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st);
-        mm<S>(b.h2, 128, r.w3, r.n_out, 128, b.rad, r.n_out, c.n_e, r.b3, 0, st);
+        mm_ap<S>(b.h2, r.w3, r.n_out, 128, b.rad, r.n_out, c.n_e, r.b3, st);
     }
-    // g_rad lives in wRAD [n_e, n_out]; accumulates into g_gauss
-    template <class S> void radial_bwd(const RadialW& r, const Chunk& c, const EB<S>& b, cudaStream_t st) {
-        mm<S>(b.rad, r.n_out, r.w3_t, 128, r.n_out, b.h2, 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_bwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, c.n_e, st);
-        mm<S>(b.h2, 128, r.w2_t, 128, 128, b.h1, 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_bwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, c.n_e, st);
-        mm<S>(b.h1, 128, r.w1g_t, NB, 128, gp<S>(g_gauss, c.e0 * NB), NB, c.n_e, nullptr, 1, st);
+    // g_rad: [n_e, n_out] A operand; accumulates into g_gauss.  u1 / u2 are the forward pre-activations.
+    template <class S> void radial_bwd(const RadialW& r, const Chunk& c, const EB<S>& b, AP<S> g_rad, cudaStream_t st) {
+        mm_ap<S>(g_rad, r.w3_t, 128, r.n_out, b.h2f, 128, c.n_e, nullptr, st);                  // dL/dh_2
+        launch_ln_silu_bwd_t<S>(b.u2, b.h2f, b.gu, r.ln2w, r.ln2b, c.n_e, st);                   // dL/du_2
+        mm_ap<S>(b.gu, r.w2_t, 128, 128, b.h2f, 128, c.n_e, nullptr, st);                        // dL/dh_1
+        // dL/du_1 stays fp32: the last GEMM (N = 64, accumulating) runs on the in-kernel-split path
+        launch_ln_silu_bwd_t<S>(b.u1, b.h2f, ap<S>(wH1, 0, 0, false), r.ln1w, r.ln1b, c.n_e, st);
+        mm<S>(b.h1f, 128, r.w1g_t, NB, 128, gp<S>(g_gauss, c.e0 * NB), NB, c.n_e, nullptr, 1, st);
     }
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)
     template <class S>
@@ -416,20 +492,20 @@ struct umab_engine {
         radial_fwd<S>(w.rad, c, b, st);
         timed(P_GATHER, P * (c.n_e * 15512.0 + c.n_nodes * 4608.0), st, [&] {
             launch_gather_rotate_scale_t<S>(n1, src.i(), tgt.i(), gp<S>(wig), b.rad, c.e0, c.n_e, b.a0, b.a1, b.a2, st); });
-        mm<S>(b.a0, 768, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, 0, st);
-        mm<S>(b.a1, 512, w.c1m1, 512, 512, b.y1, 512, 2LL * c.n_e, nullptr, 0, st);
-        mm<S>(b.a2, 256, w.c1m2, 256, 256, b.y2, 256, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_COMBINE, P * c.n_e * 13312.0, st, [&] {
+        mm_ap<S>(b.a0, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, st);
+        mm_ap<S>(b.a1, w.c1m1, 512, 1024, b.y1, 512, c.n_e, nullptr, st);
+        mm_ap<S>(b.a2, w.c1m2, 256, 512, b.y2, 256, c.n_e, nullptr, st);
+        timed(P_COMBINE, P * c.n_e * (YW + 1152) * 4.0, st, [&] {
             launch_combine_gate_fwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, st); });
-        mm<S>(b.b0, 384, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, 0, st);
-        mm<S>(b.b1, 256, w.c2m1, 512, 256, b.z1, 512, 2LL * c.n_e, nullptr, 0, st);
-        mm<S>(b.b2, 128, w.c2m2, 256, 128, b.z2, 256, 2LL * c.n_e, nullptr, 0, st);
+        mm_ap<S>(b.b0, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, st);
+        mm_ap<S>(b.b1, w.c2m1, 512, 512, b.z1, 512, c.n_e, nullptr, st);
+        mm_ap<S>(b.b2, w.c2m2, 256, 256, b.z2, 256, c.n_e, nullptr, st);
         if (dbg_on && chunks.size() == 1) {
             std::string p = "l" + std::to_string(layer) + ".";
             save_dbg(p + "rad", plane(b.rad, 0), (size_t)c.n_e * 1536, st);
             save_dbg(p + "y0", plane(b.y0, 0), (size_t)c.n_e * 640, st);
-            save_dbg(p + "y1", plane(b.y1, 0), (size_t)c.n_e * 1024, st);
-            save_dbg(p + "y2", plane(b.y2, 0), (size_t)c.n_e * 512, st);
+            save_dbg(p + "y1", plane(b.y1, 0), (size_t)c.n_e * 512, st);
+            save_dbg(p + "y2", plane(b.y2, 0), (size_t)c.n_e * 256, st);
             save_dbg(p + "z0", plane(b.z0, 0), (size_t)c.n_e * 384, st);
         }
     }
@@ -439,21 +515,21 @@ struct umab_engine {
         const double P = planes<S>();
         if (store_mode) radial_fwd<S>(w.rad, c, b, st);          // only the radial weights are recomputed
         else edge_fwd_chunk<S>(w, n1, c, layer, false, st);      // recompute everything up to Z
-        timed(P_ROTBACK_BWD, P * (c.n_e * (2 * 7680.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
+        timed(P_ROTBACK_BWD, P * (c.n_e * (2 * ZW * 4.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
             launch_rotate_back_bwd_t<S>(0, b.z0, b.z1, b.z2, tgt.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0, c.n_e, g_out,
-                                        b.z0, b.z1, b.z2, gp<S>(g_env), gp<S>(g_wig), st); });
-        mm<S>(b.z0, 384, w.c2m0_t, 384, 384, b.b0, 384, c.n_e, nullptr, 0, st);
-        mm<S>(b.z1, 512, w.c2m1_t, 256, 512, b.b1, 256, 2LL * c.n_e, nullptr, 0, st);
-        mm<S>(b.z2, 256, w.c2m2_t, 128, 256, b.b2, 128, 2LL * c.n_e, nullptr, 0, st);
-        timed(P_COMBINE_BWD, P * c.n_e * (8704.0 * 2 + 4608.0), st, [&] {
-            launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, b.y0, b.y1, b.y2, st); });
-        mm<S>(b.y0, 640, w.c1m0_t, 768, 640, b.a0, 768, c.n_e, nullptr, 0, st);
-        mm<S>(b.y1, 512, w.c1m1_t, 512, 512, b.a1, 512, 2LL * c.n_e, nullptr, 0, st);
-        mm<S>(b.y2, 256, w.c1m2_t, 256, 256, b.a2, 256, 2LL * c.n_e, nullptr, 0, st);
+                                        b.gz0, b.gz1, b.gz2, gp<S>(g_env), gp<S>(g_wig), st); });
+        mm_ap<S>(b.gz0, w.c2m0_t, 384, 384, b.gb0, 384, c.n_e, nullptr, st);
+        mm_ap<S>(b.gz1, w.c2m1_t, 512, 512, b.gb1, 512, c.n_e, nullptr, st);
+        mm_ap<S>(b.gz2, w.c2m2_t, 256, 256, b.gb2, 256, c.n_e, nullptr, st);
+        timed(P_COMBINE_BWD, P * c.n_e * (YW * 4.0 * 2 + 4608.0), st, [&] {
+            launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.gb0, b.gb1, b.gb2, b.gy0, b.gy1, b.gy2, st); });
+        mm_ap<S>(b.gy0, w.c1m0_t, 768, 640, b.ga0, 768, c.n_e, nullptr, st);
+        mm_ap<S>(b.gy1, w.c1m1_t, 1024, 512, b.ga1, 1024, c.n_e, nullptr, st);
+        mm_ap<S>(b.gy2, w.c1m2_t, 512, 256, b.ga2, 512, c.n_e, nullptr, st);
         timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0), st, [&] {
-            launch_gather_rotate_bwd_t<S>(n1, row_ptr.i(), src.i(), gp<S>(wig), b.rad, c.e0, c.node0, c.n_nodes, b.a0, b.a1,
-                                          b.a2, b.rad, gp<S>(Gbuf), g_n1, gp<S>(g_wig), st); });
-        radial_bwd<S>(w.rad, c, b, st);
+            launch_gather_rotate_bwd_t<S>(n1, row_ptr.i(), src.i(), gp<S>(wig), b.rad, c.e0, c.node0, c.n_nodes, b.ga0, b.ga1,
+                                          b.ga2, b.grad, gp<S>(Gbuf), g_n1, gp<S>(g_wig), st); });
+        radial_bwd<S>(w.rad, c, b, b.grad, st);
     }
 
     // ------------------------------------------------------------------ full evaluation
@@ -463,13 +539,13 @@ struct umab_engine {
     void evaluate(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
         if (!finalized) throw CudaError("umab_finalize_weights has not been called");
         timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(plane(pos, 0), nimg, st); });
-        plan_chunks<S>();
         const int L = cfg.num_layers;
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
         const bool want_f = (bool)forces;
+        want_adjoint = want_f;
         {
-            const double need = (double)n_edges * 4096.0 * 4.0 * L * planes<S>();
+            const double need = (double)n_edges * (YW + ZW) * 4.0 * L * planes<S>();
             double budget = (double)cfg.store_bytes;
             if (cfg.store_bytes == 0) {
                 size_t fr = 0, tot = 0;
@@ -479,10 +555,11 @@ struct umab_engine {
             store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
             if (store_mode) {
                 ystore.resize(L); zstore.resize(L);
-                for (auto& b : ystore) b.ensure<S>(ne * 2176 * 4);
-                for (auto& b : zstore) b.ensure<S>(ne * 1920 * 4);
+                for (auto& b : ystore) b.ensure<S>(ne * YW * 4);
+                for (auto& b : zstore) b.ensure<S>(ne * ZW * 4);
             }
         }
+        plan_chunks<S>();
         vec.ensure<S>(ne * 12); dist.ensure<S>(ne * 4); env.ensure<S>(ne * 4); wig.ensure<S>(ne * WIG * 4);
         gauss.ensure<S>(ne * NB * 4);
         timed(P_GEOMETRY, planes<S>() * (double)n_edges * (24.0 + 4.0 * (5 + WIG + NB)), st, [&] {
@@ -520,7 +597,7 @@ struct umab_engine {
             for (const Chunk& c : chunks) {
                 edge_fwd_chunk<S>(w, gp<S>(nbuf), c, l, true, st);
                 const EB<S> b = bufs_for<S>(l, c);
-                timed(P_ROTBACK, planes<S>() * (c.n_e * 7828.0 + c.n_nodes * 9216.0), st, [&] {
+                timed(P_ROTBACK, planes<S>() * (c.n_e * (ZW * 4.0 + 148.0) + c.n_nodes * 9216.0), st, [&] {
                     launch_rotate_back_reduce_t<S>(0, b.z0, b.z1, b.z2, row_ptr.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0,
                                                    c.node0, c.n_nodes, gp<S>(xs[l]), gp<S>(x1s[l]), st); });
             }
@@ -582,9 +659,9 @@ struct umab_engine {
             const EB<S> b = bufs_for<S>(-1, c);
             radial_fwd<S>(ed_rad, c, b, st);
             launch_rotate_back_bwd_t<S>(1, b.rad, gnull<S>(), gnull<S>(), tgt.i(), gp<S>(wig), gp<S>(env),
-                                        1.0f / cfg.edge_degree_rescale, c.e0, c.n_e, gp<S>(gx), b.rad, gnull<S>(),
-                                        gnull<S>(), gp<S>(g_env), gp<S>(g_wig), st);
-            radial_bwd<S>(ed_rad, c, b, st);
+                                        1.0f / cfg.edge_degree_rescale, c.e0, c.n_e, gp<S>(gx), b.ged, anull<S>(),
+                                        anull<S>(), gp<S>(g_env), gp<S>(g_wig), st);
+            radial_bwd<S>(ed_rad, c, b, b.ged, st);
         }
         save_dbg("g_gauss", g_gauss.v.p, (size_t)n_edges * NB, st);
         save_dbg("g_env", g_env.v.p, (size_t)n_edges, st);
@@ -598,12 +675,13 @@ struct umab_engine {
 
     ~umab_engine() {
         tc_cache_destroy(tc_cache);
+        tc2_cache_destroy(tc2_cache);
         for (auto& kv : weights) kv.second.buf.release();
         DevBuf* all[] = {&z1, &pos_own, &zt, &deg, &thr, &row_ptr, &src, &tgt, &odeg, &sptr, &cursor, &stmp, &sedge,
                          &node_e, &e_dev, &f_dev, &t_dev, &df_dev};
         for (DevBuf* b : all) b->release();
         TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
-                        &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2};
+                        &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
         for (TBuf* b : tall) b->release();
         for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore}) for (auto& b : *v) b.release();
         for (auto& kv : dbg) kv.second.first.release();
@@ -671,6 +749,7 @@ int32_t umab_set_weight(umab_engine* e, const char* name, const float* host, siz
     UMAB_CUDA(cudaMemcpy(w.buf.p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
     e->finalized = false;
     tc_cache_clear(e->tc_cache);                 // bf16 planes are derived from the fp32 weights
+    tc2_cache_clear(e->tc2_cache);
     UMAB_CATCH
 }
 
@@ -788,7 +867,11 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     GemmArgs g;
     g.A = a_dev; g.lda = k; g.W = w_dev; g.ldw = k; g.Cmat = c_dev; g.ldc = n; g.bias = bias_dev;
     g.M = (int)m; g.N = n; g.K = k;
-    if (mode == 1 || mode == 2) {
+    if (mode == 3 || mode == 4) {
+        // TMA-fed kernel (gemm_tc2.cu), k block 64 / 32; the fp32 activation is split into planes for the call
+        if (!gemm_tc2_supported(g, mode == 3 ? 64 : 32)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
+        gemm_tc2(g, (cudaStream_t)stream, nullptr, mode == 3 ? 64 : 32);
+    } else if (mode == 1 || mode == 2) {
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
         // mode 1: weight planes rebuilt on every call (never cached by pointer);
         // mode 2: planes cached by pointer for timing loops (the caller keeps W alive and unchanged)
@@ -797,6 +880,48 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     } else {
         gemm_simt(g, (cudaStream_t)stream);
     }
+    UMAB_CATCH
+}
+
+int32_t umab_gemm_bench(int32_t mode, const float* a_dev, const float* w_dev, float* c_dev, int64_t m, int32_t n,
+                        int32_t k, int32_t iters, double* ms_per_iter, void* stream) {
+    UMAB_TRY
+    if (!a_dev || !w_dev || !c_dev || !ms_per_iter || iters <= 0) throw CudaError("bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmArgs g;
+    g.A = a_dev; g.lda = k; g.W = w_dev; g.ldw = k; g.Cmat = c_dev; g.ldc = n; g.M = (int)m; g.N = n; g.K = k;
+    static TcPlaneCache* c1 = tc_cache_create();
+    static Tc2Cache* c2 = tc2_cache_create();
+    __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+    const int bk = mode == 4 ? 32 : 64;
+    if (mode == 3 || mode == 4) {
+        if (!gemm_tc2_supported(g, bk)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
+        UMAB_CUDA(cudaMalloc(&hi, (size_t)m * k * 2));
+        UMAB_CUDA(cudaMalloc(&lo, (size_t)m * k * 2));
+        tc2_split(a_dev, (long long)m * k, hi, lo, st);
+        g.A_hi = hi; g.A_lo = lo;
+    } else if (mode == 1 || mode == 2) {
+        if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
+    }
+    auto run = [&] {
+        if (mode == 3 || mode == 4) gemm_tc2(g, st, c2, bk);
+        else if (mode == 1 || mode == 2) gemm_tc(g, st, c1);
+        else gemm_simt(g, st);
+    };
+    run();                                             // warm-up: weight planes, tensor maps
+    cudaEvent_t e0, e1;
+    UMAB_CUDA(cudaEventCreate(&e0));
+    UMAB_CUDA(cudaEventCreate(&e1));
+    UMAB_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) run();
+    UMAB_CUDA(cudaEventRecord(e1, st));
+    UMAB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    UMAB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_iter = (double)ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tc_cache_clear(c1); tc2_cache_clear(c2);          // the caller's W / A pointers are not stable across calls
+    if (hi) { cudaFree(hi); cudaFree(lo); }
     UMAB_CATCH
 }
 

@@ -17,7 +17,7 @@ constexpr float LN_EPS = 1e-5f;
 // S = float (energy/forces) or D1 (value + tangent, analytic Hessian columns)
 template <class S>
 __global__ void __launch_bounds__(256)
-ln_silu_fwd_kernel(GP<S> u, GP<S> h, const float* __restrict__ gamma, const float* __restrict__ beta,
+ln_silu_fwd_kernel(GP<S> u, AP<S> h, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ bias, const float* __restrict__ t_src, const float* __restrict__ t_tgt,
                    const int* __restrict__ z, const int* __restrict__ src, const int* __restrict__ tgt, int rows) {
     using V = typename VecOf<S>::type;
@@ -52,10 +52,10 @@ ln_silu_fwd_kernel(GP<S> u, GP<S> h, const float* __restrict__ gamma, const floa
     h.st4(off, vsilu(y));
 }
 
-// g: in = dL/dh, out = dL/du (in place)
+// g = dL/dh  ->  out = dL/du (the A operand of the next adjoint GEMM; never aliases g)
 template <class S>
 __global__ void __launch_bounds__(256)
-ln_silu_bwd_kernel(GP<S> u, GP<S> g, const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
+ln_silu_bwd_kernel(GP<S> u, GP<S> g, AP<S> out, const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
     using V = typename VecOf<S>::type;
     const int row = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -75,7 +75,7 @@ ln_silu_bwd_kernel(GP<S> u, GP<S> g, const float* __restrict__ gamma, const floa
         y.v = f4add(f4mul(y.v, ga), be);
         y.d = f4mul(y.d, ga);
     }
-    V gx = vmul(g.ld4(off), vdsilu(y));
+    V gx = vmul(g.ldg4(off), vdsilu(y));
     if constexpr (std::is_same<S, float>::value) {
         gx = f4mul(gx, ga);
     } else {
@@ -85,13 +85,13 @@ ln_silu_bwd_kernel(GP<S> u, GP<S> g, const float* __restrict__ gamma, const floa
     S m1 = warp_sum(vhsum(gx)) * (1.0f / 128.0f);
     S m2 = warp_sum(vdot(gx, xh)) * (1.0f / 128.0f);
     V o = vscale(vsub(vsubs(gx, m1), vscale(xh, m2)), rstd);
-    g.st4(off, o);
+    out.st4(off, o);
 }
 
 }  // namespace
 
 template <class S>
-void launch_ln_silu_fwd_t(GP<S> u, GP<S> h, const float* gamma, const float* beta, const float* bias,
+void launch_ln_silu_fwd_t(GP<S> u, AP<S> h, const float* gamma, const float* beta, const float* bias,
                           const float* t_src, const float* t_tgt, const int* z, const int* src, const int* tgt,
                           int rows, cudaStream_t st) {
     if (rows <= 0) return;
@@ -99,16 +99,16 @@ void launch_ln_silu_fwd_t(GP<S> u, GP<S> h, const float* gamma, const float* bet
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
-void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, const float* gamma, const float* beta, int rows, cudaStream_t st) {
+void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st) {
     if (rows <= 0) return;
-    ln_silu_bwd_kernel<S><<<(rows + 7) / 8, 256, 0, st>>>(u, g, gamma, beta, rows);
+    ln_silu_bwd_kernel<S><<<(rows + 7) / 8, 256, 0, st>>>(u, g, out, gamma, beta, rows);
     UMAB_LAUNCH_CHECK();
 }
-template void launch_ln_silu_fwd_t<float>(GP<float>, GP<float>, const float*, const float*, const float*, const float*,
+template void launch_ln_silu_fwd_t<float>(GP<float>, AP<float>, const float*, const float*, const float*, const float*,
                                           const float*, const int*, const int*, const int*, int, cudaStream_t);
-template void launch_ln_silu_fwd_t<D1>(GP<D1>, GP<D1>, const float*, const float*, const float*, const float*,
+template void launch_ln_silu_fwd_t<D1>(GP<D1>, AP<D1>, const float*, const float*, const float*, const float*,
                                        const float*, const int*, const int*, const int*, int, cudaStream_t);
-template void launch_ln_silu_bwd_t<float>(GP<float>, GP<float>, const float*, const float*, int, cudaStream_t);
-template void launch_ln_silu_bwd_t<D1>(GP<D1>, GP<D1>, const float*, const float*, int, cudaStream_t);
+template void launch_ln_silu_bwd_t<float>(GP<float>, GP<float>, AP<float>, const float*, const float*, int, cudaStream_t);
+template void launch_ln_silu_bwd_t<D1>(GP<D1>, GP<D1>, AP<D1>, const float*, const float*, int, cudaStream_t);
 
 }  // namespace umab

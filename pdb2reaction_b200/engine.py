@@ -28,7 +28,7 @@ GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
 EXPORTS = (
     "umab_abi_version", "umab_last_error", "umab_create", "umab_destroy", "umab_set_weight",
     "umab_finalize_weights", "umab_set_system", "umab_build_graph", "umab_graph_counts",
-    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm",
+    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
 )
 
@@ -77,6 +77,7 @@ def load_library(path: Optional[str] = None):
     lib.umab_energy_forces_host.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.umab_forces_jvp.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.umab_gemm.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.umab_gemm_bench.argtypes = [i32, vp, vp, vp, i64, i32, i32, i32, ctypes.POINTER(ctypes.c_double), vp]
     lib.umab_debug_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.umab_profile.argtypes = [vp, i32]
@@ -109,7 +110,8 @@ def prepare_engine_weights(merged: Dict[str, torch.Tensor], arch: UMAArch) -> Di
     Adds, for every GEMM weight W [out, in], its transpose ``*_t`` (the backward contracts with
     W instead of W^T and the kernels only implement  A . W^T), and for every radial MLP the
     split first layer: ``w1g`` (Gaussian columns) + per-element tables ``t_src``/``t_tgt``
-    (= embedding @ W1_part^T), so the [E, 320] x_edge matrix is never materialised.
+    (= embedding @ W1_part^T), so the [E, 320] x_edge matrix is never materialised.  The m > 0 SO(2)
+    weights are expanded to their complex block form [[W_r, -W_i], [W_i, W_r]].
     """
     nb, ce = arch.num_distance_basis, arch.edge_channels
     out: Dict[str, torch.Tensor] = {}
@@ -157,6 +159,12 @@ def prepare_engine_weights(merged: Dict[str, torch.Tensor], arch: UMAArch) -> Di
                 w = merged[key + ".weight"]
                 if w.dim() != 2:
                     raise ValueError(f"{key}.weight is not merged (shape {tuple(w.shape)})")
+                if m > 0:
+                    # fold the SO(2) (+m, -m) combination into the weight: [x(+m) | x(-m)] @ Wc^T = [o_r | o_i]
+                    # (same FLOPs, half the conv output to write and re-read; twin: oracle/staged.so2_complex_weight)
+                    ho = w.shape[0] // 2
+                    wr, wi = w[:ho].float(), w[ho:].float()
+                    w = torch.cat([torch.cat([wr, -wi], 1), torch.cat([wi, wr], 1)], 0)
                 put_t(key + ".weight", w)
                 if m == 0:
                     put(key + ".bias", merged[key + ".bias"])
@@ -176,7 +184,7 @@ class _DevPtr:
 
 
 MAX_ATOMS_PER_CALL = 49152        # node-state memory bound of one library call (~100 KB per atom)
-STORE_BYTES_PER_EDGE = 4096 * 4 * 4   # conv outputs kept for the backward: 16.4 KB per edge and layer, 4 layers
+STORE_BYTES_PER_EDGE = 2560 * 4 * 4   # conv outputs kept for the backward: 1408 + 1152 floats = 10.2 KB per edge and layer, 4 layers
 
 
 class UmabEngine:
@@ -368,3 +376,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _check(lib, lib.umab_gemm(mode, a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                               c.data_ptr(), m, n, k, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return c
+
+
+def gemm_bench(a: torch.Tensor, w: torch.Tensor, mode: int, iters: int = 5) -> float:
+    """Kernel-only milliseconds per launch of one GEMM shape (CUDA events inside the library)."""
+    lib = load_library()
+    a, w = a.contiguous(), w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    ms = ctypes.c_double(0.0)
+    _check(lib, lib.umab_gemm_bench(mode, a.data_ptr(), w.data_ptr(), c.data_ptr(), m, n, k, iters, ctypes.byref(ms),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return ms.value

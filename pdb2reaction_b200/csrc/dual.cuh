@@ -123,6 +123,10 @@ UMAB_MAP4(vsigmoid, s_sigmoid)
 UMAB_MAP4(vdsilu, s_dsilu)
 #undef UMAB_MAP4
 
+// L2 prefetch of the 16 bytes at p (a warp issuing it with consecutive lanes pulls 512 B = 4 lines): overlaps the
+// DRAM latency of data a later phase / loop iteration will load, without holding destination registers
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------ global pointers (value plane [+ tangent plane])
 template <class S> struct GP;
 template <> struct GP<float> {
@@ -133,6 +137,7 @@ template <> struct GP<float> {
     // read-only path: only for tensors the kernel never writes (not for in-place operands)
     __device__ __forceinline__ float4 ldg4(long long i) const { return __ldg(reinterpret_cast<const float4*>(p + i)); }
     __device__ __forceinline__ float ldg(long long i) const { return __ldg(p + i); }
+    __device__ __forceinline__ void prefetch(long long i) const { prefetch_l2(p + i); }
     __device__ __forceinline__ void st4(long long i, float4 x) const { *reinterpret_cast<float4*>(p + i) = x; }
     __device__ __forceinline__ float ld(long long i) const { return p[i]; }
     __device__ __forceinline__ void st(long long i, float x) const { p[i] = x; }
@@ -149,6 +154,7 @@ template <> struct GP<D1> {
         return D4{__ldg(reinterpret_cast<const float4*>(v + i)), __ldg(reinterpret_cast<const float4*>(d + i))};
     }
     __device__ __forceinline__ D1 ldg(long long i) const { return D1{__ldg(v + i), __ldg(d + i)}; }
+    __device__ __forceinline__ void prefetch(long long i) const { prefetch_l2(v + i); prefetch_l2(d + i); }
     __device__ __forceinline__ void st4(long long i, D4 x) const {
         *reinterpret_cast<float4*>(v + i) = x.v;
         *reinterpret_cast<float4*>(d + i) = x.d;
@@ -171,6 +177,7 @@ template <> struct AP<float> {
     }
     __device__ __forceinline__ void st4(long long i, float4 x) const {
         if (hi) {
+            // (pairing lanes for one 16-byte store per lane instead of two 8-byte ones was measured: no gain)
             uint2 h, l;
             split4(x, h, l);
             *reinterpret_cast<uint2*>(hi + i) = h;

@@ -184,9 +184,18 @@ gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __re
     const long long rp = (long long)el * RAD1 + lane * 4;
     const long long i0 = (long long)el * 768 + lane * 4, i1 = (long long)el * 1024 + lane * 4,
                     i2 = (long long)el * 512 + lane * 4;
+    // the l blocks below are latency-serialised phases: pull every row they will read into L2 up front
+    const int node_s = src[e], node_t = tgt[e];
+#pragma unroll
+    for (int q = 0; q < RAD1 / 128; ++q) rad.prefetch(rp + q * 128);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        x.prefetch((long long)node_s * (9 * C) + r * C + lane * 4);
+        x.prefetch((long long)node_t * (9 * C) + r * C + lane * 4);
+    }
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-        const int node = half == 0 ? src[e] : tgt[e];
+        const int node = half == 0 ? node_s : node_t;
         const long long xp = (long long)node * (9 * C) + lane * 4;
         // m-primary row k of the rotated message: times its radial weight, into the operand buffer of its m block
         auto put = [&](int k, V y) {
@@ -227,6 +236,39 @@ gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __re
     }
 }
 
+// Variant with all 18 node rows and the whole Wigner record in flight (more memory-level parallelism per warp,
+// 128 registers -> 2 CTAs per SM).  Selected at run time (UMAB_GRS_VARIANT=1) for A/B measurements.
+template <class S>
+__global__ void __launch_bounds__(256, min_blocks<S>(2))
+gather_rotate_scale_wide_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
+                                long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
+    using V = typename VecOf<S>::type;
+    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (el >= n_e) return;
+    const long long e = e0 + el;
+    const WigReg<S> w = load_wig<S>(wig, e);
+    const long long rp = (long long)el * RAD1 + lane * 4;
+    const long long i0 = (long long)el * 768 + lane * 4, i1 = (long long)el * 1024 + lane * 4,
+                    i2 = (long long)el * 512 + lane * 4;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int node = half == 0 ? src[e] : tgt[e];
+        const long long xp = (long long)node * (9 * C) + lane * 4;
+        V xr[9], yl[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) xr[r] = x.ldg4(xp + r * C);
+        rot_fwd(w, xr, yl);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const V o = vmul(yl[to_m(k)], rad.ldg4(rp + r_off(k) + half * C));
+            if (a_buf(k) == 0) A0.st4(i0 + a_off(k) + half * C, o);
+            else if (a_buf(k) == 1) A1.st4(i1 + a_off(k) + half * C, o);
+            else A2.st4(i2 + a_off(k) + half * C, o);
+        }
+    }
+}
+
 // adjoint: one warp per TARGET node of the chunk, looping over its CSR row.
 //   g_rad [E,1536] (A operand of the radial adjoint GEMM; never aliases rad);  G[e] = dL/dx[src] contribution [9,128] (l-primary);
 //   g_x[i] = sum over the row of the target-half contributions;  g_wig[e] += ...
@@ -245,8 +287,25 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
     for (int r = 0; r < 9; ++r) acc_i[r] = vzero<V>();
     const long long xi_p = (long long)i * (9 * C) + lane * 4;
 
-    for (long long e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+    const long long e_end = row_ptr[i + 1];
+    for (long long e = row_ptr[i]; e < e_end; ++e) {
         const long long el = e - e0;
+        if (e + 1 < e_end) {
+            // the loop is a chain of dependent DRAM round trips: pull the next edge's rows into L2 meanwhile
+            const long long en = el + 1;
+            if (lane < 9) wig.prefetch((e + 1) * WIG + lane * 4);
+#pragma unroll
+            for (int q = 0; q < RAD1 / 128; ++q) rad.prefetch(en * RAD1 + q * 128 + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) gA0.prefetch(en * 768 + q * 128 + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) gA1.prefetch(en * 1024 + q * 128 + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gA2.prefetch(en * 512 + q * 128 + lane * 4);
+            const long long xn = (long long)src[e + 1] * (9 * C) + lane * 4;
+#pragma unroll
+            for (int r = 0; r < 9; ++r) x.prefetch(xn + r * C);
+        }
         const WigReg<S> w = load_wig<S>(wig, e);
         const long long rp = el * RAD1 + lane * 4;
         const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
@@ -437,7 +496,20 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
     V acc[9];
 #pragma unroll
     for (int r = 0; r < 9; ++r) acc[r] = vzero<V>();
-    for (long long e = row_ptr[i]; e < row_ptr[i + 1]; ++e) {
+    const long long e_end = row_ptr[i + 1];
+    for (long long e = row_ptr[i]; e < e_end; ++e) {
+        if (e + 1 < e_end) {
+            const long long en = e + 1 - e0;
+            if (lane < 9) wig.prefetch((e + 1) * WIG + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) Z0.prefetch(en * 384 + q * 128 + lane * 4);
+            if (MODE == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Z1.prefetch(en * 512 + q * 128 + lane * 4);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) Z2.prefetch(en * 256 + q * 128 + lane * 4);
+            }
+        }
         const WigReg<S> w = load_wig<S>(wig, e);
         V zl[9], y[9];
         load_zl<MODE, S, V>(Z0, Z1, Z2, e - e0, lane, zl);
@@ -510,7 +582,9 @@ template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
                                   AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st) {
     if (n_e <= 0) return;
-    gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    static const bool wide = [] { const char* e = getenv("UMAB_GRS_VARIANT"); return e && atoi(e) == 1; }();
+    if (wide) gather_rotate_scale_wide_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    else gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>

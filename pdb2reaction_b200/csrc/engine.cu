@@ -470,18 +470,24 @@ struct umab_engine {
     template <class S> void radial_fwd(const RadialW& r, const Chunk& c, const EB<S>& b, cudaStream_t st) {
         const long long e0 = c.e0;
         mm<S>(gp<S>(gauss, e0 * NB), NB, r.w1g, 128, NB, b.u1, 128, c.n_e, nullptr, 0, st);
-        launch_ln_silu_fwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st);
+        const double lnb = planes<S>() * c.n_e * 128.0 * 4.0;     // one [n_e,128] fp32 tensor
+        timed(P_LN_SILU, 3 * lnb, st, [&] {
+            launch_ln_silu_fwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st); });
         mm_ap<S>(b.h1, r.w2, 128, 128, b.u2, 128, c.n_e, r.b2, st);
-        launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st);
+        timed(P_LN_SILU, 2 * lnb, st, [&] {
+            launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st); });
         mm_ap<S>(b.h2, r.w3, r.n_out, 128, b.rad, r.n_out, c.n_e, r.b3, st);
     }
     // g_rad: [n_e, n_out] A operand; accumulates into g_gauss.  u1 / u2 are the forward pre-activations.
     template <class S> void radial_bwd(const RadialW& r, const Chunk& c, const EB<S>& b, AP<S> g_rad, cudaStream_t st) {
         mm_ap<S>(g_rad, r.w3_t, 128, r.n_out, b.h2f, 128, c.n_e, nullptr, st);                  // dL/dh_2
-        launch_ln_silu_bwd_t<S>(b.u2, b.h2f, b.gu, r.ln2w, r.ln2b, c.n_e, st);                   // dL/du_2
+        const double lnb = planes<S>() * c.n_e * 128.0 * 4.0;
+        timed(P_LN_SILU, 3 * lnb, st, [&] {
+            launch_ln_silu_bwd_t<S>(b.u2, b.h2f, b.gu, r.ln2w, r.ln2b, c.n_e, st); });           // dL/du_2
         mm_ap<S>(b.gu, r.w2_t, 128, 128, b.h2f, 128, c.n_e, nullptr, st);                        // dL/dh_1
         // dL/du_1 stays fp32: the last GEMM (N = 64, accumulating) runs on the in-kernel-split path
-        launch_ln_silu_bwd_t<S>(b.u1, b.h2f, ap<S>(wH1, 0, 0, false), r.ln1w, r.ln1b, c.n_e, st);
+        timed(P_LN_SILU, 3 * lnb, st, [&] {
+            launch_ln_silu_bwd_t<S>(b.u1, b.h2f, ap<S>(wH1, 0, 0, false), r.ln1w, r.ln1b, c.n_e, st); });
         mm<S>(b.h1f, 128, r.w1g_t, NB, 128, gp<S>(g_gauss, c.e0 * NB), NB, c.n_e, nullptr, 1, st);
     }
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)

@@ -1,11 +1,16 @@
 """Summarise an `ncu --set full` capture of one kernel family into profiles/traffic.json:
 average DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) and pipe utilisation.
-usage: python tools/ncu_traffic.py <report.ncu-rep> <kernel-key> <algorithmic-bytes-per-launch or 0> <note>"""
+usage: python tools/ncu_traffic.py <report.ncu-rep | raw.csv> <kernel-key> <algorithmic-bytes-per-launch or 0> <note>"""
 import csv, io, json, os, subprocess, sys
 
 rep, key, alg, note = sys.argv[1], sys.argv[2], float(sys.argv[3]), sys.argv[4]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+while rows and (not rows[0] or rows[0][0] != "ID"):
+    rows.pop(0)
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}

@@ -59,7 +59,7 @@ typedef struct umab_config {
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 4
+#define UMAB_ABI_VERSION 5
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);
@@ -71,6 +71,10 @@ UMAB_API void umab_destroy(umab_engine* e);
 UMAB_API int32_t umab_set_weight(umab_engine* e, const char* name, const float* host, size_t numel);
 /* Verify that every parameter the kernels need is present with the expected size. */
 UMAB_API int32_t umab_finalize_weights(umab_engine* e);
+
+/* Run-time options.  "neighbor_mode": 0 = auto (shared-memory cell list from 128 atoms per image, brute
+ * force below), 1 = brute force, 2 = cell list; both searches return the identical edge list. */
+UMAB_API int32_t umab_set_option(umab_engine* e, const char* name, int64_t value);
 
 /* Atomic numbers of ONE image (host, n_atoms ints); all images share them. */
 UMAB_API int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms);

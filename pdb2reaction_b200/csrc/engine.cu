@@ -194,6 +194,8 @@ struct umab_engine {
     long long n_edges = 0;
     int zt_img = -1;
     DevBuf pos_own, zt, deg, thr, row_ptr, src, tgt, odeg, sptr, cursor, stmp, sedge;
+    DevBuf cgrid, ccount, cstart, catoms, acell;       // cell list of the neighbour search
+    int neighbor_mode = 0;                             // 0 auto (cell list from 128 atoms per image), 1 brute force, 2 cell list
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<Chunk> chunks;
     // geometry
@@ -373,7 +375,19 @@ struct umab_engine {
         }
         deg.ensure(sizeof(int) * n_nodes); thr.ensure(sizeof(float) * n_nodes);
         row_ptr.ensure(sizeof(int) * (n_nodes + 1));
-        launch_neighbor_count(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, deg.i(), thr.f(), st);
+        const bool cells = neighbor_mode == 2 || (neighbor_mode == 0 && n_atoms >= 128);
+        int cap_cells = 64;
+        while (cap_cells < n_atoms / 2 && cap_cells < 65536) cap_cells *= 2;
+        if (cells) {
+            cgrid.ensure(cell_grid_bytes() * nimg); ccount.ensure(sizeof(int) * (size_t)nimg * cap_cells);
+            cstart.ensure(sizeof(int) * (size_t)nimg * (cap_cells + 1));
+            catoms.ensure(sizeof(int) * n_nodes); acell.ensure(sizeof(int) * n_nodes);
+            launch_cell_list(pos, nimg, n_atoms, cfg.cutoff, cap_cells, cgrid.p, ccount.i(), acell.i(), cstart.i(), catoms.i(), st);
+            launch_neighbor_cell_count(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, cap_cells, cgrid.p, cstart.i(),
+                                       catoms.i(), deg.i(), thr.f(), st);
+        } else {
+            launch_neighbor_count(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, deg.i(), thr.f(), st);
+        }
         launch_scan(deg.i(), row_ptr.i(), n_nodes, st);
         size_t need = sizeof(int) * (n_nodes + 1);
         if (need > h_pinned_cap) {
@@ -387,7 +401,11 @@ struct umab_engine {
         if (n_edges > 0x7fffffffLL / 40) throw CudaError("too many edges in one batch: split it on the host");
         size_t ne = (size_t)std::max<long long>(n_edges, 1);
         src.ensure(sizeof(int) * ne); tgt.ensure(sizeof(int) * ne);
-        launch_neighbor_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, thr.f(), row_ptr.i(), src.i(), tgt.i(), st);
+        if (cells)
+            launch_neighbor_cell_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, cap_cells, cgrid.p, cstart.i(),
+                                      catoms.i(), thr.f(), row_ptr.i(), src.i(), tgt.i(), st);
+        else
+            launch_neighbor_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, thr.f(), row_ptr.i(), src.i(), tgt.i(), st);
         odeg.ensure(sizeof(int) * n_nodes); sptr.ensure(sizeof(int) * (n_nodes + 1)); cursor.ensure(sizeof(int) * n_nodes);
         stmp.ensure(sizeof(int) * ne); sedge.ensure(sizeof(int) * ne);
         launch_source_csr(src.i(), (int)n_edges, n_nodes, odeg.i(), sptr.i(), cursor.i(), stmp.i(), sedge.i(), st);
@@ -684,7 +702,7 @@ struct umab_engine {
         tc2_cache_destroy(tc2_cache);
         for (auto& kv : weights) kv.second.buf.release();
         DevBuf* all[] = {&z1, &pos_own, &zt, &deg, &thr, &row_ptr, &src, &tgt, &odeg, &sptr, &cursor, &stmp, &sedge,
-                         &node_e, &e_dev, &f_dev, &t_dev, &df_dev};
+                         &cgrid, &ccount, &cstart, &catoms, &acell, &node_e, &e_dev, &f_dev, &t_dev, &df_dev};
         for (DevBuf* b : all) b->release();
         TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
                         &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
@@ -776,6 +794,19 @@ int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms) 
     UMAB_CUDA(cudaMemcpy(e->z1.p, z_host, sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
     e->n_atoms = n_atoms;
     e->zt_img = -1;
+    UMAB_CATCH
+}
+
+int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
+    UMAB_TRY
+    if (!e || !name) throw CudaError("null argument");
+    const std::string n(name);
+    if (n == "neighbor_mode") {
+        if (value < 0 || value > 2) throw CudaError("neighbor_mode: 0 auto, 1 brute force, 2 cell list");
+        e->neighbor_mode = (int)value;
+    } else {
+        throw CudaError("unknown option: " + n);
+    }
     UMAB_CATCH
 }
 

@@ -10,6 +10,16 @@ void launch_neighbor_count(const float* pos, int n_img, int n_atoms, float cutof
 void launch_neighbor_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, const float* thr,
                           const int* row_ptr, int* src, int* tgt, cudaStream_t st);
 void launch_scan(const int* in, int* out, int n, cudaStream_t st);
+// shared-memory cell-list search (same edge list as the brute-force kernels)
+size_t cell_grid_bytes();
+void launch_cell_list(const float* pos, int n_img, int n_atoms, float cutoff, int cap_cells, void* grid,
+                      int* cell_count, int* atom_cell, int* cell_start, int* cell_atoms, cudaStream_t st);
+void launch_neighbor_cell_count(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int cap_cells,
+                                const void* grid, const int* cell_start, const int* cell_atoms, int* deg, float* thr,
+                                cudaStream_t st);
+void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int cap_cells,
+                               const void* grid, const int* cell_start, const int* cell_atoms, const float* thr,
+                               const int* row_ptr, int* src, int* tgt, cudaStream_t st);
 void launch_source_csr(const int* src, int n_edges, int n_nodes, int* odeg, int* sptr, int* cursor, int* tmp,
                        int* sedge, cudaStream_t st);
 

@@ -19,7 +19,7 @@ from .arch import UMAArch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -27,7 +27,7 @@ GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
 # every symbol include/umab.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "umab_abi_version", "umab_last_error", "umab_create", "umab_destroy", "umab_set_weight",
-    "umab_finalize_weights", "umab_set_system", "umab_build_graph", "umab_graph_counts",
+    "umab_finalize_weights", "umab_set_option", "umab_set_system", "umab_build_graph", "umab_graph_counts",
     "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
 )
@@ -77,6 +77,7 @@ def load_library(path: Optional[str] = None):
     lib.umab_energy_forces_host.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.umab_forces_jvp.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.umab_gemm.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.umab_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.umab_gemm_bench.argtypes = [i32, vp, vp, vp, i64, i32, i32, i32, ctypes.POINTER(ctypes.c_double), vp]
     lib.umab_debug_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -328,6 +329,12 @@ class UmabEngine:
         _check(self.lib, self.lib.umab_graph_copy(self._h, src.data_ptr(), tgt.data_ptr(), None, self._stream_ptr()))
         torch.cuda.current_stream(self.device).synchronize()
         return torch.stack([src.long(), tgt.long()]).cpu()
+
+    NEIGHBOR_MODES = {"auto": 0, "brute": 1, "cell": 2}
+
+    def set_neighbor_mode(self, mode: str):
+        """'auto' (shared-memory cell list from 128 atoms per image), 'brute' or 'cell'; identical edge lists."""
+        _check(self.lib, self.lib.umab_set_option(self._h, b"neighbor_mode", self.NEIGHBOR_MODES[mode]))
 
     def graph_counts(self):
         nn_, ne_ = ctypes.c_int64(), ctypes.c_int64()

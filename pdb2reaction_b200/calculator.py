@@ -64,30 +64,32 @@ MAX_ATOMS_PER_CALL = 49152      # FD-Hessian batching unit (the engine sub-batch
 # weights: process-wide cache (the reference re-creates calculators constantly)
 # ======================================================================================
 _state_lock = threading.Lock()
-_state_cache: Dict[str, Dict[str, torch.Tensor]] = {}
+_state_cache: Dict[str, tuple] = {}
 _engine_cache: Dict[tuple, Any] = {}
 
 
-def load_model_state(model: str, arch: UMAArch) -> Dict[str, torch.Tensor]:
-    """Un-merged state dict for ``model``.
+def load_model_state(model: str, arch: UMAArch, task_name: str = "omol"):
+    """-> (un-merged state dict, ``checkpoint.EnergyTransform``) for ``model``.
 
-    ``model`` is either a path to a ``torch.save``d state dict in this package's naming
-    (``weights.init_uma_weights``) or a model ID such as ``"uma-s-1p1"``.  The reference downloads
-    the ID from a gated HF repo (``uma_pysis.py:246-250``); offline that is impossible, so an ID
-    resolves to ``$UMAB_WEIGHTS`` if set, else to RANDOM-INIT weights of the uma-s-1p1
-    architecture (seed 0) with a warning -- energies are then not physical.
+    ``model`` is either a path -- a fairchem ``MLIPInferenceCheckpoint`` / fairchem-named state dict
+    (converted by ``checkpoint.load_checkpoint``, no fairchem install needed) or a ``torch.save``d state
+    dict in this package's naming (``weights.init_uma_weights``) -- or a model ID such as
+    ``"uma-s-1p1"``.  The reference downloads the ID from a gated HF repo (``uma_pysis.py:246-250``);
+    offline that is impossible, so an ID resolves to ``$UMAB_WEIGHTS`` if set, else to RANDOM-INIT
+    weights of the uma-s-1p1 architecture (seed 0) with a warning -- energies are then not physical.
     """
+    from .checkpoint import EnergyTransform, load_checkpoint
     path = model if os.path.exists(str(model)) else os.environ.get("UMAB_WEIGHTS")
-    key = f"file:{path}" if path else f"random:{model}:{arch.num_experts}"
+    key = f"file:{path}:{task_name}" if path else f"random:{model}:{arch.num_experts}"
     with _state_lock:
         if key not in _state_cache:
             if path:
-                _state_cache[key] = torch.load(path, map_location="cpu")
+                _state_cache[key] = load_checkpoint(path, arch, task_name=task_name)
             else:
                 warnings.warn(
                     f"no checkpoint available for model {model!r} (offline): using random-init "
                     "uma-s-1p1-architecture weights, seed 0", RuntimeWarning, stacklevel=3)
-                _state_cache[key] = _weights.init_uma_weights(arch, seed=0)
+                _state_cache[key] = (_weights.init_uma_weights(arch, seed=0), EnergyTransform())
         return _state_cache[key]
 
 
@@ -118,12 +120,15 @@ class CudaBackend:
         key_base = (str(model), tuple(self.z), int(charge), int(spin), str(task_name),
                     None if radius is None else float(radius), None if max_neigh is None else int(max_neigh))
         self.engines = []
+        # normaliser + element references of the prediction unit; identity for random-init
+        _, self.transform = load_model_state(model, self.arch, task_name)
+        self._e_const = self.transform.constant_for(self.z)
         for d in self.devices:
             key = key_base + (d,)
             with _state_lock:
                 eng = _engine_cache.get(key)
             if eng is None:
-                state = load_model_state(model, self.arch)
+                state, _ = load_model_state(model, self.arch, task_name)
                 merged = _weights.merge_mole(state, self.arch, self.z, charge, spin, task_name)
                 eng = UmabEngine(merged, self.z, self.arch, device=d, cutoff=radius, max_neighbors=max_neigh)
                 with _state_lock:
@@ -152,6 +157,10 @@ class CudaBackend:
             run(0)
         else:
             list(self._pool.map(run, range(len(self.engines))))
+        if not self.transform.is_identity:
+            e_out = e_out * self.transform.scale + self._e_const
+            if forces:
+                f_out *= np.float32(self.transform.scale)
         return e_out, f_out
 
     def hessian_columns(self, coord_ang: np.ndarray, dofs: Sequence[int]) -> np.ndarray:
@@ -186,6 +195,8 @@ class CudaBackend:
             run(0)
         else:
             list(self._pool.map(run, range(len(self.engines))))
+        if self.transform.scale != 1.0:
+            out *= np.float32(self.transform.scale)
         return out
 
 

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def small_model(state4, arch4, monkeypatch):
     """Route model='test-4x' to the 4-expert test weights (the default ID means 32 experts)."""
-    monkeypatch.setattr(calc_mod, "load_model_state", lambda model, arch: state4)
+    from pdb2reaction_b200.checkpoint import EnergyTransform
+    monkeypatch.setattr(calc_mod, "load_model_state", lambda model, arch, task_name="omol": (state4, EnergyTransform()))
     orig = calc_mod.CudaBackend.__init__
 
     def init(self, elem, **kw):

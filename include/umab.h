@@ -106,7 +106,8 @@ UMAB_API int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const flo
  * and roofline measurements.  mode: 0 SIMT fp32, 1 tensor-core bf16x3 (activation split in the kernel),
  * 2 same with the bf16 weight planes cached by pointer (timing loops only), 3 / 4 TMA-fed tensor-core
  * bf16x3 kernel (activation pre-split into bf16 hi/lo planes, as the pipeline's producing kernels write
- * it) with a 64 / 32 wide k block. */
+ * it) with a 64 / 32 wide k block, 5 / 6 the CTA-pair (cta_group::2, 256-row tiles) form of the same kernel
+ * with a 64 / 32 wide k block. */
 UMAB_API int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const float* bias_dev, float* c_dev,
                   int64_t m, int32_t n, int32_t k, void* stream);
 

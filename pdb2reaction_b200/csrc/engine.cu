@@ -33,7 +33,7 @@ struct Tc2Cache;                                     // gemm_tc2.cu
 Tc2Cache* tc2_cache_create();
 void tc2_cache_destroy(Tc2Cache* c);
 void tc2_cache_clear(Tc2Cache* c);
-void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk);
+void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int pair = -1);
 bool gemm_tc2_supported(const GemmArgs& a, int bk);
 void tc2_split(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
@@ -904,10 +904,12 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     GemmArgs g;
     g.A = a_dev; g.lda = k; g.W = w_dev; g.ldw = k; g.Cmat = c_dev; g.ldc = n; g.bias = bias_dev;
     g.M = (int)m; g.N = n; g.K = k;
-    if (mode == 3 || mode == 4) {
-        // TMA-fed kernel (gemm_tc2.cu), k block 64 / 32; the fp32 activation is split into planes for the call
-        if (!gemm_tc2_supported(g, mode == 3 ? 64 : 32)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
-        gemm_tc2(g, (cudaStream_t)stream, nullptr, mode == 3 ? 64 : 32);
+    if (mode >= 3 && mode <= 6) {
+        // TMA-fed kernel (gemm_tc2.cu): single-CTA with k block 64 / 32 (modes 3 / 4), CTA pair with k block 64 / 32
+        // (modes 5 / 6); the fp32 activation is split into planes for the call
+        const int bk = (mode == 3 || mode == 5) ? 64 : 32;
+        if (!gemm_tc2_supported(g, bk)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
+        gemm_tc2(g, (cudaStream_t)stream, nullptr, bk, mode >= 5 ? 1 : 0);
     } else if (mode == 1 || mode == 2) {
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
         // mode 1: weight planes rebuilt on every call (never cached by pointer);
@@ -930,8 +932,9 @@ int32_t umab_gemm_bench(int32_t mode, const float* a_dev, const float* w_dev, fl
     static TcPlaneCache* c1 = tc_cache_create();
     static Tc2Cache* c2 = tc2_cache_create();
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
-    const int bk = mode == 4 ? 32 : 64;
-    if (mode == 3 || mode == 4) {
+    const int bk = (mode == 4 || mode == 6) ? 32 : 64;
+    const bool tc2 = mode >= 3 && mode <= 6;
+    if (tc2) {
         if (!gemm_tc2_supported(g, bk)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
         UMAB_CUDA(cudaMalloc(&hi, (size_t)m * k * 2));
         UMAB_CUDA(cudaMalloc(&lo, (size_t)m * k * 2));
@@ -941,7 +944,7 @@ int32_t umab_gemm_bench(int32_t mode, const float* a_dev, const float* w_dev, fl
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
     }
     auto run = [&] {
-        if (mode == 3 || mode == 4) gemm_tc2(g, st, c2, bk);
+        if (tc2) gemm_tc2(g, st, c2, bk, mode >= 5 ? 1 : 0);
         else if (mode == 1 || mode == 2) gemm_tc(g, st, c1);
         else gemm_simt(g, st);
     };

@@ -193,6 +193,178 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  ncu on the single-CTA kernel above: the big conv shapes pull 11.4 TB/s through
+// xbar -> l1tex (l1tex__m_xbar2l1tex_read_bytes), i.e. the L2 -> SM fabric cap, at 55 % tensor-pipe activity -- with a
+// 128 x 256 tile every k block of 64 moves 32 KB of A planes + 64 KB of W planes per CTA for 12 MMAs.  Here the two
+// SMs of a TPC compute one 256 x BN tile: each CTA loads its own 128 rows of A but only HALF of the W tile (BN / 2
+// rows); the MMA, issued by the leader CTA (cluster rank 0), reads the B operand from both CTAs' shared memory and
+// accumulates rows 0-127 into the leader's TMEM and rows 128-255 into the peer's.  L2 -> SM bytes per MMA drop by a
+// third (64 KB instead of 96 KB per k block and CTA) and the smaller stage gives a third pipeline stage.
+//   full[s]       leader only: 1 arrival (leader's producer, expect_tx of BOTH CTAs' bytes); the peer's TMA loads
+//                 complete_tx on it through the cta_group::2 load form
+//   empty[s]      one per CTA, armed by the leader's tcgen05.commit multicast
+//   tmem_full[b]  one per CTA, same multicast commit;  tmem_empty[b]  leader only, 2 x EPI_WARPS (remote) arrivals
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
+                     const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+                     const __grid_constant__ CUtensorMap tm_c, Tc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int ROW_BYTES = BK * 2;
+    constexpr uint32_t A_PLANE = BM * ROW_BYTES;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int S = p.stages;
+    const int BN = p.BN;
+    const int HN = BN / 2;                                       // W rows held by each CTA of the pair
+    const uint32_t w_plane = (uint32_t)HN * ROW_BYTES;
+    const uint32_t stage_bytes = 2u * A_PLANE + 2u * w_plane;
+    const uint32_t stg_base = base + (uint32_t)S * stage_bytes;
+    const uint32_t bar_base = stg_base + EPI_WARPS * STG_BYTES;
+    auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return a_hi(s) + A_PLANE; };
+    auto w_hi = [&](int s) { return a_hi(s) + 2u * A_PLANE; };
+    auto w_lo = [&](int s) { return w_hi(s) + w_plane; };
+    auto full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+    auto empty = [&](int s) { return bar_base + 8u * (uint32_t)(S + s); };
+    auto tmem_full = [&](int b) { return bar_base + 8u * (uint32_t)(2 * S + b); };
+    auto tmem_empty = [&](int b) { return bar_base + 8u * (uint32_t)(2 * S + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x / 2, npairs = (int)gridDim.x / 2;
+    const int nkb = p.K / BK;
+    const int ntn = p.N / BN;
+    const int num_tiles = ntn * ((p.M + 2 * BM - 1) / (2 * BM));        // 256-row tiles
+    const int my_tiles = (num_tiles - pair + npairs - 1) / npairs;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                    // both CTAs' barriers are initialised before any remote arrive / TMA complete_tx
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own A rows, own half of the W tile; bytes land on the leader's barrier
+        if (lane == 0) {
+            int g = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int tile = pair + lt * npairs;
+                const int n0 = (tile % ntn) * BN + (int)rank * HN;
+                const int m0 = (tile / ntn) * (2 * BM) + (int)rank * BM;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % S;
+                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    if (rank == 0) mbar_arrive_expect_tx(full(s), 2u * stage_bytes);
+                    const uint32_t fb = mapa_cluster(full(s), 0);
+                    tma_load_2d_pair(a_hi(s), &tm_ah, fb, kb * BK, m0);
+                    tma_load_2d_pair(w_hi(s), &tm_wh, fb, kb * BK, n0);
+                    tma_load_2d_pair(a_lo(s), &tm_al, fb, kb * BK, m0);
+                    tma_load_2d_pair(w_lo(s), &tm_wl, fb, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: leader CTA only
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_bf16_pair(BN);
+            int g = 0;
+            for (int lt = 0; lt < my_tiles; ++lt) {
+                const int ab = lt & 1;
+                mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % S;
+                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                    mbar_wait(full(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t dah = make_smem_desc<ROW_BYTES>(a_hi(s)), dal = make_smem_desc<ROW_BYTES>(a_lo(s));
+                    const uint64_t dwh = make_smem_desc<ROW_BYTES>(w_hi(s)), dwl = make_smem_desc<ROW_BYTES>(w_lo(s));
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j) {
+                        const uint64_t adv = (uint64_t)(j * 2);
+                        umma_bf16_pair(d_tmem, dah + adv, dwh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_bf16_pair(d_tmem, dah + adv, dwl + adv, idesc, 1u);
+                        umma_bf16_pair(d_tmem, dal + adv, dwh + adv, idesc, 1u);
+                    }
+                    umma_commit_pair(empty(s));       // frees the stage in both CTAs
+                }
+                umma_commit_pair(tmem_full(ab));      // accumulator halves of both CTAs complete
+            }
+        }
+    } else {
+        // ===================== epilogue warps (both CTAs): own 128 rows of the pair tile
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t stg = stg_base + (uint32_t)ew * STG_BYTES;
+        const uint32_t row_addr = stg + (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const int nch = BN / 32;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int tile = pair + lt * npairs;
+            const int n0 = (tile % ntn) * BN;
+            const int mrow0 = (tile / ntn) * (2 * BM) + (int)rank * BM + q * 32;
+            const int ab = lt & 1;
+            mbar_wait(tmem_full(ab), ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)(ab * p.tmem_cols) + ((uint32_t)(q * 32) << 16);
+            for (int ch = half; ch < nch; ch += 2) {
+                uint32_t rr[32];
+                tmem_ld32_async(taddr + (uint32_t)(ch * 32), rr);
+                float4 bv[8];
+                if (p.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+                }
+                tmem_ld_wait();
+                if (lane == 0) tma_store_wait_read0();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                           __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+                    if (p.bias) o = f4add(o, bv[j]);
+                    const uint32_t addr = row_addr + ((((uint32_t)j) ^ sw) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && mrow0 < p.M) {
+                    tma_store_2d(&tm_c, stg, n0 + ch * 32, mrow0);
+                    tma_store_commit();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(mapa_cluster(tmem_empty(ab), 0));
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    // neither CTA may leave (or free TMEM) while its partner can still read its shared memory / arrive on its barriers
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
+    }
+}
+
 // fp32 [rows, K] -> bf16 hi / lo planes (weights once per engine; activations only in the unit-test entry)
 __global__ void split_planes2_kernel(const float* __restrict__ w, long long n, __nv_bfloat16* __restrict__ hi,
                                      __nv_bfloat16* __restrict__ lo) {
@@ -251,7 +423,8 @@ void make_map2(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* p
 
 struct Planes2 {
     __nv_bfloat16* hi = nullptr; __nv_bfloat16* lo = nullptr;
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi, tm_lo;             // box = [bn, bk]: the whole W tile (single-CTA kernel)
+    CUtensorMap tm_hi_half, tm_lo_half;   // box = [bn / 2, bk]: the half each CTA of a pair loads
     int bn = 0;
 };
 
@@ -326,6 +499,8 @@ Planes2 build_planes2(const float* W, int N, int K, int bk, cudaStream_t st) {
     const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     make_map2(&p.tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.hi, N, K, (long long)K * 2, p.bn, bk, sw);
     make_map2(&p.tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.lo, N, K, (long long)K * 2, p.bn, bk, sw);
+    make_map2(&p.tm_hi_half, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.hi, N, K, (long long)K * 2, p.bn / 2, bk, sw);
+    make_map2(&p.tm_lo_half, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.lo, N, K, (long long)K * 2, p.bn / 2, bk, sw);
     return p;
 }
 
@@ -339,6 +514,40 @@ void launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const Planes2& pl,
         UMAB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     });
     gemm_tc2_kernel<BK><<<grid, T2_THREADS, smem, st>>>(ah, al, pl.tm_hi, pl.tm_lo, cm, p);
+    UMAB_LAUNCH_CHECK();
+}
+
+// CTAs of the pair kernel that can be resident at once (2 x the co-resident clusters; 0 = cluster launch unsupported)
+template <int BK>
+int pair_max_ctas(int dev) {
+    static int cached[16] = {0};
+    static std::once_flag once[16];
+    std::call_once(once[dev & 15], [dev] {
+        UMAB_CUDA(cudaFuncSetAttribute(gemm_tc2_pair_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        int n_sm = 0;
+        UMAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_sm & ~1)); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = SMEM_LIMIT;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, gemm_tc2_pair_kernel<BK>, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+        cached[dev & 15] = std::min(2 * ncl, n_sm & ~1);
+    });
+    return cached[dev & 15];
+}
+
+template <int BK>
+void launch_tc2_pair(const CUtensorMap& ah, const CUtensorMap& al, const Planes2& pl, const CUtensorMap& cm,
+                     const Tc2Params& p, size_t smem, long long pair_tiles, cudaStream_t st) {
+    int dev = 0;
+    UMAB_CUDA(cudaGetDevice(&dev));
+    const int cap = pair_max_ctas<BK>(dev);
+    if (cap < 2) throw CudaError("gemm_tc2: the CTA-pair kernel cannot be launched on this device");
+    dim3 grid((unsigned)std::min<long long>(2 * pair_tiles, cap));
+    gemm_tc2_pair_kernel<BK><<<grid, T2_THREADS, smem, st>>>(ah, al, pl.tm_hi_half, pl.tm_lo_half, cm, p);
     UMAB_LAUNCH_CHECK();
 }
 
@@ -358,9 +567,22 @@ int tc2_pick_bk(int N, int K) {
     return 64;
 }
 
-// bk = 64 or 32 (0: per-shape choice).  cache == nullptr: everything is built for this call only (unit-test entry).
-void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk) {
-    if (bk == 0) bk = tc2_pick_bk(a.N, a.K);
+// CTA-pair kernel by default (UMAB_TC2_PAIR=0 selects the single-CTA kernel)
+bool tc2_pair_default() {
+    static const bool on = [] {
+        const char* e = getenv("UMAB_TC2_PAIR");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
+// bk = 64 or 32 (0: per-shape choice); pair = 1 / 0: CTA-pair / single-CTA kernel (-1: default).
+// cache == nullptr: everything is built for this call only (unit-test entry).
+void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int pair) {
+    // default: the CTA-pair kernel with 64-wide k blocks; the two shapes it does not win (measured,
+    // profiles/r01_gemm_pair_shapes.txt) stay on the single-CTA kernel
+    if (pair < 0) pair = (tc2_pair_default() && !((a.N == 128 && a.K == 64) || (a.N == 384 && a.K == 128))) ? 1 : 0;
+    if (bk == 0) bk = pair ? 64 : tc2_pick_bk(a.N, a.K);
     if (bk != 64 && bk != 32) throw CudaError("gemm_tc2: bk must be 64 or 32");
     if (!gemm_tc2_supported(a, bk)) throw CudaError("gemm_tc2: unsupported shape");
     int dev = 0;
@@ -396,7 +618,7 @@ void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk) {
     }
     Tc2Params p;
     p.bias = a.bias; p.M = a.M; p.N = a.N; p.K = a.K; p.BN = pl.bn;
-    const int stage_bytes = 2 * BM * bk * 2 + 2 * pl.bn * bk * 2;
+    const int stage_bytes = 2 * BM * bk * 2 + 2 * (pair ? pl.bn / 2 : pl.bn) * bk * 2;
     const int fixed = EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 8 * (2 * 8 + 5) + 64;
     p.stages = std::max(2, std::min(8, (SMEM_LIMIT - fixed) / stage_bytes));
     int cols = 32;
@@ -408,7 +630,11 @@ void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk) {
     if (!n_sm[dev & 15]) UMAB_CUDA(cudaDeviceGetAttribute(&n_sm[dev & 15], cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (long long)(a.N / pl.bn) * ((a.M + BM - 1) / BM);
     dim3 grid((unsigned)std::min<long long>(tiles, n_sm[dev & 15]));
-    if (bk == 64) launch_tc2<64>(ah, al, pl, cm, p, smem, grid, st);
+    if (pair) {
+        const long long pair_tiles = (long long)(a.N / pl.bn) * ((a.M + 2 * BM - 1) / (2 * BM));
+        if (bk == 64) launch_tc2_pair<64>(ah, al, pl, cm, p, smem, pair_tiles, st);
+        else launch_tc2_pair<32>(ah, al, pl, cm, p, smem, pair_tiles, st);
+    } else if (bk == 64) launch_tc2<64>(ah, al, pl, cm, p, smem, grid, st);
     else launch_tc2<32>(ah, al, pl, cm, p, smem, grid, st);
     if (!cache || tmp_hi) {
         UMAB_CUDA(cudaStreamSynchronize(st));

@@ -59,7 +59,7 @@ typedef struct umab_config {
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 5
+#define UMAB_ABI_VERSION 6
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);
@@ -129,6 +129,22 @@ UMAB_API int32_t umab_profile(umab_engine* e, int32_t enable);
 UMAB_API int32_t umab_profile_read(umab_engine* e, int32_t cat, double* ms, int64_t* launches, double* work,
                                    double* bytes);
 UMAB_API const char* umab_profile_name(int32_t cat);
+
+/* ---- Hessian assembly / vibrational pre-processing on the device (no engine handle; current CUDA device).
+ *
+ * umab_hessian_fd_columns: forces_dev [2 * n_cols, dof] fp32 holds F(x + h e_k), F(x - h e_k) for k = dof_idx_dev[q];
+ * writes H[:, k] = -(F+ - F-) / (2 h_step) into hessian_dev [dof, ld] (fp64 when is_f64, else fp32).  Replaces the
+ * column loop of uma_pysis._build_fd_hessian_gpu (pdb2reaction/uma_pysis.py:652-675).
+ *
+ * umab_hessian_mw_project: in place, fp64:  H <- sym(P (S H S) P) with S = diag(inv_sqrt_m_dev [n]) and
+ * P = I - Q Q^T, q_dev [n, r] row-major orthonormal translation/rotation basis, r <= 6 (r = 0: mass-weighting and
+ * symmetrisation only).  Replaces freq._mw_projected_hessian (pdb2reaction/freq.py:159-205) and the PHVA
+ * variants (freq.py:290-335).  workspace_dev: at least umab_hessian_mw_workspace(n, r) doubles. */
+UMAB_API int32_t umab_hessian_fd_columns(const float* forces_dev, const int32_t* dof_idx_dev, int32_t n_cols, int32_t dof,
+                                         double h_step, void* hessian_dev, int64_t ld, int32_t is_f64, void* stream);
+UMAB_API int64_t umab_hessian_mw_workspace(int32_t n, int32_t r);
+UMAB_API int32_t umab_hessian_mw_project(double* hessian_dev, int32_t n, const double* inv_sqrt_m_dev, const double* q_dev,
+                                         int32_t r, double* workspace_dev, int64_t workspace_doubles, void* stream);
 
 /* Counters since creation: kernel launches issued by this library and bytes allocated. */
 UMAB_API int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_bytes);

@@ -163,6 +163,34 @@ class CudaBackend:
                 f_out *= np.float32(self.transform.scale)
         return e_out, f_out
 
+    def forces_device(self, coords_ang: np.ndarray) -> torch.Tensor:
+        """coords [B,N,3] A -> forces [B,N,3] fp32 eV/A as ONE tensor on the first GPU: shards are evaluated on
+        their GPUs and gathered device-to-device (no host copy of the results) -- feeds the on-device FD Hessian."""
+        pos = np.ascontiguousarray(coords_ang, dtype=np.float32)
+        b, n = pos.shape[0], pos.shape[1]
+        out = torch.empty((b, n, 3), dtype=torch.float32, device=self.torch_device)
+        from .sharding import shard_bounds
+        bounds = shard_bounds(b, len(self.engines))
+
+        def run(rank):
+            lo, hi = bounds[rank]
+            if hi <= lo:
+                return
+            eng = self.engines[rank]
+            dev = torch.device("cuda", eng.device)
+            with torch.cuda.device(dev):
+                _, f = eng.energy_forces(torch.from_numpy(pos[lo:hi]).to(dev), True)
+                torch.cuda.current_stream(dev).synchronize()
+                out[lo:hi].copy_(f)
+
+        if self._pool is None:
+            run(0)
+        else:
+            list(self._pool.map(run, range(len(self.engines))))
+        if self.transform.scale != 1.0:
+            out *= float(self.transform.scale)
+        return out
+
     def hessian_columns(self, coord_ang: np.ndarray, dofs: Sequence[int]) -> np.ndarray:
         """Analytic Hessian columns H[:, k] (eV/A^2, float32) for k in ``dofs``: one dual-number
         (value + tangent) pass of the forward and the hand-written backward per column, columns
@@ -321,6 +349,7 @@ class uma_pysis(Calculator):
         # all +h / -h geometries, displaced in float64 before the fp32 cast (Q3)
         per = max(1, MAX_ATOMS_PER_CALL // n_atoms) * len(getattr(core.backend, "engines", [0]))
         per = max(2, per - per % 2)
+        on_device = hasattr(core.backend, "forces_device")        # CUDA backend: the columns never visit the host
         for s in range(0, len(active_dof), per // 2):
             ks = active_dof[s:s + per // 2]
             batch = np.repeat(coord_ang[None], 2 * len(ks), axis=0)
@@ -328,6 +357,11 @@ class uma_pysis(Calculator):
                 a, c = divmod(k, 3)
                 batch[2 * q, a, c] = coord_ang[a, c] + eps_ang
                 batch[2 * q + 1, a, c] = coord_ang[a, c] - eps_ang
+            if on_device:
+                from .hessian_post import fd_hessian_columns_
+                fd_hessian_columns_(hmat, core.backend.forces_device(batch).reshape(2 * len(ks), dof),
+                                    torch.as_tensor(ks, device=dev, dtype=torch.int32), eps_ang)
+                continue
             f = core.compute_batch(batch, forces=True)["forces"].reshape(2 * len(ks), dof)
             ft = torch.from_numpy(f).to(dev, dtype=hdt)
             cols = -(ft[0::2] - ft[1::2]) / (2.0 * eps_ang)                 # [len(ks), dof]

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "neighbors.cu", "geometry.cu", "radial.cu",
-           "edge_ops.cu", "node_ops.cu"]
+           "edge_ops.cu", "node_ops.cu", "hessian_ops.cu"]
 LIB = os.path.join(HERE, "libumab.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -36,6 +36,10 @@ void tc2_cache_clear(Tc2Cache* c);
 void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int pair = -1);
 bool gemm_tc2_supported(const GemmArgs& a, int bk);
 void tc2_split(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+void launch_fd_columns(const float* f, const int* ks, int n_cols, int dof, double h_step, void* hmat, long long ldh,
+                       bool f64, cudaStream_t st);                                         // hessian_ops.cu
+size_t mw_project_workspace_doubles(int n, int r);
+void launch_mw_project(double* h, int n, const double* inv_sqrt_m, const double* q, int r, double* ws, cudaStream_t st);
 
 namespace {
 
@@ -895,6 +899,30 @@ int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const float* tange
     }
     e->evaluate<D1>(GP<D1>{const_cast<float*>(pos_dev), const_cast<float*>(tangent_dev)}, n_images, energy_dev,
                     GP<D1>{forces_dev, dforces_dev}, st);
+    UMAB_CATCH
+}
+
+int32_t umab_hessian_fd_columns(const float* forces_dev, const int32_t* dof_idx_dev, int32_t n_cols, int32_t dof,
+                                double h_step, void* hessian_dev, int64_t ld, int32_t is_f64, void* stream) {
+    UMAB_TRY
+    if (!forces_dev || !dof_idx_dev || !hessian_dev || n_cols < 0 || dof <= 0 || ld < dof || !(h_step > 0.0))
+        throw CudaError("bad argument");
+    launch_fd_columns(forces_dev, dof_idx_dev, n_cols, dof, h_step, hessian_dev, ld, is_f64 != 0, (cudaStream_t)stream);
+    UMAB_CATCH
+}
+
+int64_t umab_hessian_mw_workspace(int32_t n, int32_t r) {
+    if (n <= 0 || r < 0 || r > 6) return -1;
+    return (int64_t)mw_project_workspace_doubles(n, r);
+}
+
+int32_t umab_hessian_mw_project(double* hessian_dev, int32_t n, const double* inv_sqrt_m_dev, const double* q_dev, int32_t r,
+                                double* workspace_dev, int64_t workspace_doubles, void* stream) {
+    UMAB_TRY
+    if (!hessian_dev || !inv_sqrt_m_dev || n <= 0 || r < 0 || r > 6 || (r > 0 && (!q_dev || !workspace_dev)))
+        throw CudaError("bad argument");
+    if (r > 0 && workspace_doubles < (int64_t)mw_project_workspace_doubles(n, r)) throw CudaError("workspace too small");
+    launch_mw_project(hessian_dev, n, inv_sqrt_m_dev, q_dev, r, workspace_dev, (cudaStream_t)stream);
     UMAB_CATCH
 }
 

@@ -19,7 +19,7 @@ from .arch import UMAArch
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -30,6 +30,7 @@ EXPORTS = (
     "umab_finalize_weights", "umab_set_option", "umab_set_system", "umab_build_graph", "umab_graph_counts",
     "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
+    "umab_hessian_fd_columns", "umab_hessian_mw_workspace", "umab_hessian_mw_project",
 )
 
 
@@ -84,11 +85,16 @@ def load_library(path: Optional[str] = None):
     lib.umab_profile.argtypes = [vp, i32]
     lib.umab_profile_read.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
                                       ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.umab_hessian_fd_columns.argtypes = [vp, vp, i32, i32, ctypes.c_double, vp, i64, i32, vp]
+    lib.umab_hessian_mw_workspace.argtypes = [i32, i32]
+    lib.umab_hessian_mw_workspace.restype = i64
+    lib.umab_hessian_mw_project.argtypes = [vp, i32, vp, vp, i32, vp, i64, vp]
     lib.umab_profile_name.argtypes = [i32]
     lib.umab_profile_name.restype = ctypes.c_char_p
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("umab_last_error", "umab_destroy", "umab_abi_version", "umab_profile_name"):
+        if name not in ("umab_last_error", "umab_destroy", "umab_abi_version", "umab_profile_name",
+                        "umab_hessian_mw_workspace"):
             fn.restype = i32
     if lib.umab_abi_version() != ABI_VERSION:
         raise RuntimeError("libumab.so ABI version mismatch: rebuild the extension")

@@ -141,6 +141,32 @@ __device__ __forceinline__ void wig_grad_commit(S (&acc)[34], S scale, GP<S> g_w
     if (lane == 1) g_wig.st(o + 33, g_wig.ld(o + 33) + scale * t33);
 }
 
+// same with the old g_wig values already in registers (loaded at the top of the iteration: the DRAM round trip of the
+// read-modify-write overlaps the rest of the edge's work instead of stalling its end)
+template <class S> struct WigOld { S a, b; };
+template <class S>
+__device__ __forceinline__ WigOld<S> wig_grad_load(GP<S> g_wig, long long e, int lane) {
+    const long long o = e * WIG;
+    WigOld<S> r;
+    r.a = g_wig.ld(o + lane);
+    r.b = lane < 2 ? g_wig.ld(o + 32 + lane) : cst<S>(0.f);
+    return r;
+}
+template <class S>
+__device__ __forceinline__ void wig_grad_commit_pre(S (&acc)[34], S scale, const WigOld<S>& old, GP<S> g_wig, long long e,
+                                                    int lane) {
+    S r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = acc[i];
+    S tot = warp_transpose_sum32(r, lane);
+    S t32 = warp_sum(acc[32]);
+    S t33 = warp_sum(acc[33]);
+    const long long o = e * WIG;
+    g_wig.st(o + lane, old.a + scale * tot);
+    if (lane == 0) g_wig.st(o + 32, old.b + scale * t32);
+    if (lane == 1) g_wig.st(o + 33, old.b + scale * t33);
+}
+
 // scalars [LO, LO+N) of the Wigner record of edge e (D1 = 0..8, D2 = 9..33)
 template <class S, int LO, int N>
 __device__ __forceinline__ void load_wig_part(GP<S> wig, long long e, S* out) {
@@ -309,11 +335,14 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
         const WigReg<S> w = load_wig<S>(wig, e);
         const long long rp = el * RAD1 + lane * 4;
         const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
-        S wacc[34];
+        // target half first, then the source half, each with its own g_wig commit: the same order of additions as
+        // the split (closed-chunk) kernels below, so both forms give identical bits
 #pragma unroll
-        for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
+        for (int hh = 0; hh < 2; ++hh) {
+            const int half = 1 - hh;
+            S wacc[34];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+            for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
             const long long xp = half == 0 ? (long long)src[e] * (9 * C) + lane * 4 : xi_p;
             V xr[9], yl[9], gml[9];
             V g_rad_v[6];      // radial groups 0,1,2 (m=0 rows), 3,4 (m=1: l=1,2), 5 (m=2)
@@ -347,11 +376,92 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 #pragma unroll
                 for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
             }
+            wig_grad_commit(wacc, cst<S>(1.0f), g_wig, e, lane);
         }
-        wig_grad_commit(wacc, cst<S>(1.0f), g_wig, e, lane);
     }
 #pragma unroll
     for (int r = 0; r < 9; ++r) g_x.st4(xi_p + r * C, acc_i[r]);
+}
+
+// ---- split form for CLOSED chunks (every out-edge of a node of the chunk lies inside the chunk: whole images).
+// The source half of the adjoint is then reduced by SOURCE node as well, so the per-edge buffer G [E,9,128] and the
+// source_reduce pass disappear (9.2 KB less HBM traffic per edge and layer, 4.6 KB less memory per edge), and the
+// source rows need no gather: all out-edges of node j share x[j].
+//   HALF = 1  one warp per target node i, over its in-edges  (CSR row):       g_x[i]  = sum of target-half terms
+//   HALF = 0  one warp per source node j, over its out-edges (sedge list):    g_x[j] += sum of source-half terms
+// Both add their share of dL/dD into g_wig[e]; HALF = 1 runs first, HALF = 0 second (fixed order: deterministic).
+template <int HALF, class S, int MINB>
+__global__ void __launch_bounds__(256, min_blocks<S>(MINB))
+gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
+                              long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
+                              GP<S> g_x, GP<S> g_wig) {
+    using V = typename VecOf<S>::type;
+    const int nl = blockIdx.x * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (nl >= n_nodes) return;
+    const int i = node0 + nl;
+    V acc_i[9], xr[9];
+    const long long xi_p = (long long)i * (9 * C) + lane * 4;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) { acc_i[r] = vzero<V>(); xr[r] = x.ldg4(xi_p + r * C); }
+
+    const int k_end = ptr[i + 1];
+    for (int k = ptr[i]; k < k_end; ++k) {
+        const long long e = HALF == 1 ? (long long)k : (long long)elist[k];
+        const long long el = e - e0;
+        if (k + 1 < k_end) {
+            const long long e_n = HALF == 1 ? (long long)k + 1 : (long long)elist[k + 1];
+            const long long en = e_n - e0;
+            if (lane < 9) wig.prefetch(e_n * WIG + lane * 4);
+            else if (lane < 18) g_wig.prefetch(e_n * WIG + (lane - 9) * 4);
+#pragma unroll
+            for (int q = 0; q < RAD1 / 256; ++q) rad.prefetch(en * RAD1 + q * 256 + HALF * C + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) gA0.prefetch(en * 768 + q * 256 + HALF * C + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gA1.prefetch(en * 1024 + q * 256 + HALF * C + lane * 4);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) gA2.prefetch(en * 512 + q * 256 + HALF * C + lane * 4);
+        }
+        const WigOld<S> gw_old = wig_grad_load<S>(g_wig, e, lane);
+        const WigReg<S> w = load_wig<S>(wig, e);
+        const long long rp = el * RAD1 + lane * 4;
+        const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
+        S wacc[34];
+#pragma unroll
+        for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
+        V yl[9], gml[9];
+        V g_rad_v[6];
+        rot_fwd(w, xr, yl);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) g_rad_v[q] = vzero<V>();
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) {
+            V ga = gbufs[a_buf(kk)].ldg4(a_off(kk) + HALF * C + lane * 4);
+            V rv = rad.ldg4(rp + r_off(kk) + HALF * C);
+            const int grp_id = kk < 3 ? kk : (kk == 3 || kk == 5 ? 3 : (kk == 4 || kk == 6 ? 4 : 5));
+            g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(kk)]));
+            gml[to_m(kk)] = vmul(ga, rv);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) g_rad.st4(rp + q * 256 + HALF * C, g_rad_v[q]);
+        g_rad.st4(rp + 768 + HALF * C, g_rad_v[3]);
+        g_rad.st4(rp + 1024 + HALF * C, g_rad_v[4]);
+        g_rad.st4(rp + 1280 + HALF * C, g_rad_v[5]);
+        wig_outer_acc(wacc, gml, xr);
+        V gx[9];
+        rot_bwd(w, gml, gx);
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
+        wig_grad_commit_pre(wacc, cst<S>(1.0f), gw_old, g_wig, e, lane);
+    }
+    if (HALF == 1) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) g_x.st4(xi_p + r * C, acc_i[r]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) g_x.st4(xi_p + r * C, vadd(g_x.ldg4(xi_p + r * C), acc_i[r]));
+    }
 }
 
 // g_x[j] += sum over out-edges of j of G[e]      (linear: the Hessian path runs it once per plane)
@@ -538,6 +648,10 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
     const int lane = threadIdx.x % 32;
     if (el >= n_e) return;
     const long long e = e0 + el;
+    // the read-modify-write operands first: their DRAM round trips overlap everything below
+    const WigOld<S> gw_old = wig_grad_load<S>(g_wig, e, lane);
+    S genv_old = cst<S>(0.f);
+    if (lane == 0) genv_old = g_env.ld(e);
     const WigReg<S> w = load_wig<S>(wig, e);
     V zl[9], g[9], t[9];
     load_zl<MODE, S, V>(Z0, Z1, Z2, el, lane, zl);
@@ -551,13 +665,13 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
 #pragma unroll
     for (int r = 0; r < 9; ++r) part = part + vdot(t[r], g[r]);
     part = warp_sum(part);
-    if (lane == 0) g_env.st(e, g_env.ld(e) + part * scale);
+    if (lane == 0) g_env.st(e, genv_old + part * scale);
     // d/dD[b][a] = s * sum_c zl[b][c] g[a][c]
     S wacc[34];
 #pragma unroll
     for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
     wig_outer_acc(wacc, zl, g);
-    wig_grad_commit(wacc, s, g_wig, e, lane);
+    wig_grad_commit_pre(wacc, s, gw_old, g_wig, e, lane);
     // d/dz (m-primary rows) = s * (D g)[to_m(k)]
     rot_fwd(w, g, t);
     const long long o0 = (long long)el * 384 + lane * 4;
@@ -594,6 +708,30 @@ void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<
     if (n_nodes <= 0) return;
     gather_rotate_bwd_kernel<S><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
                                                                    gA1, gA2, g_rad, G, g_x, g_wig);
+    UMAB_LAUNCH_CHECK();
+}
+// closed chunks: target halves over the CSR rows, then source halves over the out-edge lists (no G, no source_reduce)
+template <class S>
+void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* sptr, const int* sedge, GP<S> wig, GP<S> rad,
+                                       long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
+                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
+    if (n_nodes <= 0) return;
+    // UMAB_HALF_OCC=2: 128-register build (2 CTAs per SM, some spills) for A/B measurements
+    static const bool occ2 = [] { const char* e = getenv("UMAB_HALF_OCC"); return e && atoi(e) == 2; }();
+    const dim3 grid((n_nodes + 7) / 8);
+    if (occ2) {
+        gather_rotate_bwd_half_kernel<1, S, 2><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1,
+                                                                    gA2, g_rad, g_x, g_wig);
+        UMAB_LAUNCH_CHECK();
+        gather_rotate_bwd_half_kernel<0, S, 2><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
+                                                                    g_rad, g_x, g_wig);
+    } else {
+        gather_rotate_bwd_half_kernel<1, S, 1><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1,
+                                                                    gA2, g_rad, g_x, g_wig);
+        UMAB_LAUNCH_CHECK();
+        gather_rotate_bwd_half_kernel<0, S, 1><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
+                                                                    g_rad, g_x, g_wig);
+    }
     UMAB_LAUNCH_CHECK();
 }
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st) {
@@ -644,6 +782,9 @@ void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int*
                                                   AP<S>, AP<S>, cudaStream_t);                                        \
     template void launch_gather_rotate_bwd_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, int,      \
                                                 GP<S>, GP<S>, GP<S>, AP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);       \
+    template void launch_gather_rotate_bwd_closed_t<S>(GP<S>, const int*, const int*, const int*, GP<S>, GP<S>,       \
+                                                       long long, int, int, GP<S>, GP<S>, GP<S>, AP<S>, GP<S>, GP<S>,  \
+                                                       cudaStream_t);                                                  \
     template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, AP<S>, AP<S>, AP<S>, cudaStream_t);           \
     template void launch_combine_gate_bwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, AP<S>, AP<S>, AP<S>,     \
                                                cudaStream_t);                                                         \

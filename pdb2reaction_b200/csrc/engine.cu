@@ -202,6 +202,11 @@ struct umab_engine {
     int neighbor_mode = 0;                             // 0 auto (cell list from 128 atoms per image), 1 brute force, 2 cell list
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<Chunk> chunks;
+    bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
+    static bool closed_chunks_enabled() {
+        static const bool on = [] { const char* e = getenv("UMAB_CLOSED_CHUNKS"); return !(e && atoi(e) == 0); }();
+        return on;
+    }
     // geometry
     TBuf vec, dist, env, wig, gauss, g_gauss, g_env, g_wig, g_vec;
     // nodes
@@ -423,6 +428,25 @@ struct umab_engine {
         chunks.clear();
         int node0 = 0;
         long long biggest = 0;
+        // closed chunks = whole images: every out-edge of a node of the chunk is an edge of the chunk, so the adjoint
+        // can reduce the source halves by source node inside the chunk (no per-edge G buffer, no source_reduce pass)
+        long long max_img = 0;
+        for (int b = 0; b < n_img; ++b)
+            max_img = std::max<long long>(max_img, (long long)h_pinned[(b + 1) * n_atoms] - h_pinned[b * n_atoms]);
+        chunks_closed = closed_chunks_enabled() && max_img <= cap;
+        if (chunks_closed) {
+            int b0 = 0;
+            while (b0 < n_img) {
+                const long long e0 = h_pinned[b0 * n_atoms];
+                int b1 = b0 + 1;
+                while (b1 < n_img && (long long)h_pinned[(b1 + 1) * n_atoms] - e0 <= cap) ++b1;
+                Chunk c{b0 * n_atoms, (b1 - b0) * n_atoms, e0, (int)(h_pinned[b1 * n_atoms] - e0)};
+                chunks.push_back(c);
+                biggest = std::max<long long>(biggest, c.n_e);
+                b0 = b1;
+            }
+            node0 = n_nodes;
+        }
         while (node0 < n_nodes) {
             long long e0 = h_pinned[node0];
             int n1 = node0;
@@ -554,6 +578,11 @@ struct umab_engine {
         mm_ap<S>(b.gy0, w.c1m0_t, 768, 640, b.ga0, 768, c.n_e, nullptr, st);
         mm_ap<S>(b.gy1, w.c1m1_t, 1024, 512, b.ga1, 1024, c.n_e, nullptr, st);
         mm_ap<S>(b.gy2, w.c1m2_t, 512, 256, b.ga2, 512, c.n_e, nullptr, st);
+        if (chunks_closed)
+            timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 6 * 144.0 + 8.0) + c.n_nodes * 5 * 4608.0), st, [&] {
+                launch_gather_rotate_bwd_closed_t<S>(n1, row_ptr.i(), sptr.i(), sedge.i(), gp<S>(wig), b.rad, c.e0, c.node0,
+                                                     c.n_nodes, b.ga0, b.ga1, b.ga2, b.grad, g_n1, gp<S>(g_wig), st); });
+        else
         timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0), st, [&] {
             launch_gather_rotate_bwd_t<S>(n1, row_ptr.i(), src.i(), gp<S>(wig), b.rad, c.e0, c.node0, c.n_nodes, b.ga0, b.ga1,
                                           b.ga2, b.grad, gp<S>(Gbuf), g_n1, gp<S>(g_wig), st); });
@@ -652,7 +681,7 @@ struct umab_engine {
         // ================= backward: dE_total/dpos
         gx.ensure<S>(nf); gx1.ensure<S>(nf); gn.ensure<S>(nf); ggp.ensure<S>((size_t)n_nodes * 2 * H * 4);
         gs1.ensure<S>((size_t)n_nodes * H * 4);
-        Gbuf.ensure<S>(ne * 9 * C * 4);
+        if (!chunks_closed) Gbuf.ensure<S>(ne * 9 * C * 4);
         g_gauss.ensure<S>(ne * NB * 4); g_env.ensure<S>(ne * 4); g_wig.ensure<S>(ne * WIG * 4); g_vec.ensure<S>(ne * 12);
         zero<S>(g_gauss, ne * NB * 4, st);
         zero<S>(g_env, ne * 4, st);
@@ -675,7 +704,7 @@ struct umab_engine {
             // Edgewise adjoint
             launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);         // recompute n1
             for (const Chunk& c : chunks) edge_bwd_chunk<S>(w, gp<S>(nbuf), c, l, gp<S>(gx1), gp<S>(gn), st);
-            timed(P_SRC_REDUCE, planes<S>() * (n_edges * 4612.0 + n_nodes * 9216.0), st, [&] {
+            if (!chunks_closed) timed(P_SRC_REDUCE, planes<S>() * (n_edges * 4612.0 + n_nodes * 9216.0), st, [&] {
                 for (int k = 0; k < planes<S>(); ++k)
                     launch_source_reduce(plane(gp<S>(Gbuf), k), sptr.i(), sedge.i(), n_nodes, plane(gp<S>(gn), k), st); });
             save_dbg("l" + std::to_string(l) + ".g_n1", gn.v.p, (size_t)n_nodes * 9 * C, st);

@@ -32,9 +32,10 @@ fd_columns_kernel(const float* __restrict__ f, const int* __restrict__ ks, int n
     if (t >= (long long)n_cols * dof) return;
     const int q = (int)(t / dof), i = (int)(t % dof);
     // the reference's arithmetic, in the Hessian dtype T: col = -(Fp - Fm) / (2.0 * eps)   (uma_pysis.py:668-670);
-    // torch's CUDA division of a tensor by a host scalar multiplies by the reciprocal formed in T -- so do we
+    // torch's CUDA division of a tensor by a host scalar multiplies by the scalar's reciprocal, formed in double
+    // and rounded to T (measured: x / 0.002 == x * 500.0f bit for bit) -- so do we
     const T fp = (T)f[(long long)(2 * q) * dof + i], fm = (T)f[(long long)(2 * q + 1) * dof + i];
-    const T inv = (T)1 / (T)two_h;
+    const T inv = (T)(1.0 / two_h);
     h[(long long)i * ldh + ks[q]] = -(fp - fm) * inv;
 }
 

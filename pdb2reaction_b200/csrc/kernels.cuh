@@ -49,6 +49,10 @@ template <class S>
 void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<S> wig, GP<S> rad, long long e0,
                                 int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                                 GP<S> g_x, GP<S> g_wig, cudaStream_t st);
+template <class S>
+void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* sptr, const int* sedge, GP<S> wig, GP<S> rad,
+                                       long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
+                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st);
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st);
 template <class S>
 void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st);

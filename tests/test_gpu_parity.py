@@ -71,6 +71,23 @@ def test_edge_chunking_does_not_change_the_result(built_lib, state4, arch4):
     assert np.array_equal(e1, e2) and np.array_equal(f1, f2)
 
 
+def test_closed_chunks_equal_open_chunks(built_lib, state4, arch4):
+    """Whole-image (closed) chunks reduce the source halves of the edge adjoint by source node inside the chunk (no
+    per-edge G buffer); node-range (open) chunks keep G + source_reduce.  Same additions in the same order: same bits."""
+    elem, imgs = synth.make_string(60, 5, 21)
+    pos = imgs.astype(np.float32)
+    eng, _, _ = _engine(state4, arch4, elem)                                   # one closed chunk
+    n_e = eng.graph(torch.from_numpy(pos).cuda())[0].shape[0]
+    per_img = n_e // 5
+    per_edge = 9600 * 4                                                          # upper bound of the workspace per edge
+    eng_two, _, _ = _engine(state4, arch4, elem, workspace_bytes=int(2.5 * per_img) * per_edge)    # closed, 2 images / chunk
+    eng_open, _, _ = _engine(state4, arch4, elem, workspace_bytes=int(0.4 * per_img) * per_edge)   # open: image > chunk
+    e0, f0 = eng.energy_forces_host(pos)
+    for other in (eng_two, eng_open):
+        e1, f1 = other.energy_forces_host(pos)
+        assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
+
+
 def test_store_mode_equals_recompute_mode(built_lib, state4, arch4):
     """Keeping the conv outputs for the backward (store mode) or recomputing them must give the
     same bits: the same kernels run on the same data in the same order."""

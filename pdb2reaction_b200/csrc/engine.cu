@@ -172,7 +172,8 @@ struct DeviceGuard {
 constexpr int YW = 640 + 512 + 256;      // conv-1 outputs per edge: m=0 | m=1 (o_r|o_i) | m=2 (p_r|p_i)
 constexpr int ZW = 384 + 512 + 256;      // conv-2 outputs per edge
 constexpr size_t EDGE_WS_FLOATS = 2304 + YW + 1152 + ZW + 1536 + 4 * 128;   // 8064 per edge
-constexpr size_t EDGE_WS_EXTRA_RECOMPUTE = YW + ZW;   // adjoint operands g_Y / g_Z when Y / Z live in the workspace
+constexpr size_t EDGE_WS_EXTRA_RECOMPUTE = YW + ZW;
+constexpr int STORE_FLOATS = YW + ZW + 1536 + 2 * 128;   // per edge and layer in store mode: Y, Z, rad, u1, u2   // adjoint operands g_Y / g_Z when Y / Z live in the workspace
 
 }  // namespace
 }  // namespace umab
@@ -203,6 +204,10 @@ struct umab_engine {
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
     std::vector<Chunk> chunks;
     bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
+    static bool store_radial_enabled() {               // UMAB_STORE_RADIAL=0: recompute the radial MLP in the backward (A/B)
+        static const bool on = [] { const char* e = getenv("UMAB_STORE_RADIAL"); return !(e && atoi(e) == 0); }();
+        return on;
+    }
     static bool closed_chunks_enabled() {
         static const bool on = [] { const char* e = getenv("UMAB_CLOSED_CHUNKS"); return !(e && atoi(e) == 0); }();
         return on;
@@ -219,6 +224,9 @@ struct umab_engine {
     // store mode: conv-1 / conv-2 outputs of every layer are kept for the backward instead of being
     // recomputed (16.4 KB per edge and layer of HBM) when they fit `store_bytes`
     std::vector<TBuf> ystore, zstore;
+    // ... and so are the radial weights rad [E,1536] and the two radial pre-activations u1 / u2 [E,128]: the backward
+    // then recomputes nothing at all (7.2 KB more per edge and layer)
+    std::vector<TBuf> rstore, u1store, u2store;
     bool store_mode = false;
     bool want_adjoint = false;                        // this evaluation runs the backward (forces requested)
     // host staging for umab_energy_forces_host
@@ -508,7 +516,13 @@ struct umab_engine {
         b.gz2 = ap<S>(gzb, cc * (384 + 512), cc * 256, sp);
         b.grad = ap<S>(gyb, 0, cc * 1536, sp);       // written after the conv-1 adjoint GEMMs have consumed g_Y
         b.ged = ap<S>(gyb, 0, cc * 384, sp);
-        b.rad = gp<S>(wRAD); b.u1 = gp<S>(wU1); b.u2 = gp<S>(wU2); b.h1f = gp<S>(wH1); b.h2f = gp<S>(wH2);
+        if (stored && store_radial_enabled()) {
+            b.rad = gp<S>(rstore[layer], c.e0 * 1536); b.u1 = gp<S>(u1store[layer], c.e0 * 128);
+            b.u2 = gp<S>(u2store[layer], c.e0 * 128);
+        } else {
+            b.rad = gp<S>(wRAD); b.u1 = gp<S>(wU1); b.u2 = gp<S>(wU2);
+        }
+        b.h1f = gp<S>(wH1); b.h2f = gp<S>(wH2);
         b.h1 = ap<S>(wH1, 0, cc * 128, sp); b.h2 = ap<S>(wH2, 0, cc * 128, sp); b.gu = ap<S>(wH1, 0, cc * 128, sp);
         return b;
     }
@@ -565,8 +579,8 @@ struct umab_engine {
     void edge_bwd_chunk(const LayerW& w, GP<S> n1, const Chunk& c, int layer, GP<S> g_out, GP<S> g_n1, cudaStream_t st) {
         const EB<S> b = bufs_for<S>(layer, c);
         const double P = planes<S>();
-        if (store_mode) radial_fwd<S>(w.rad, c, b, st);          // only the radial weights are recomputed
-        else edge_fwd_chunk<S>(w, n1, c, layer, false, st);      // recompute everything up to Z
+        if (!store_mode) edge_fwd_chunk<S>(w, n1, c, layer, false, st);      // recompute everything up to Z
+        else if (!store_radial_enabled()) radial_fwd<S>(w.rad, c, b, st);
         timed(P_ROTBACK_BWD, P * (c.n_e * (2 * ZW * 4.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
             launch_rotate_back_bwd_t<S>(0, b.z0, b.z1, b.z2, tgt.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0, c.n_e, g_out,
                                         b.gz0, b.gz1, b.gz2, gp<S>(g_env), gp<S>(g_wig), st); });
@@ -602,7 +616,7 @@ struct umab_engine {
         const bool want_f = (bool)forces;
         want_adjoint = want_f;
         {
-            const double need = (double)n_edges * (YW + ZW) * 4.0 * L * planes<S>();
+            const double need = (double)n_edges * (store_radial_enabled() ? STORE_FLOATS : YW + ZW) * 4.0 * L * planes<S>();
             double budget = (double)cfg.store_bytes;
             if (cfg.store_bytes == 0) {
                 size_t fr = 0, tot = 0;
@@ -611,9 +625,14 @@ struct umab_engine {
             }
             store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
             if (store_mode) {
-                ystore.resize(L); zstore.resize(L);
+                ystore.resize(L); zstore.resize(L); rstore.resize(L); u1store.resize(L); u2store.resize(L);
                 for (auto& b : ystore) b.ensure<S>(ne * YW * 4);
                 for (auto& b : zstore) b.ensure<S>(ne * ZW * 4);
+                if (store_radial_enabled()) {
+                    for (auto& b : rstore) b.ensure<S>(ne * 1536 * 4);
+                    for (auto& b : u1store) b.ensure<S>(ne * 128 * 4);
+                    for (auto& b : u2store) b.ensure<S>(ne * 128 * 4);
+                }
             }
         }
         plan_chunks<S>();
@@ -740,7 +759,7 @@ struct umab_engine {
         TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
                         &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
         for (TBuf* b : tall) b->release();
-        for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore}) for (auto& b : *v) b.release();
+        for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore, &rstore, &u1store, &u2store}) for (auto& b : *v) b.release();
         for (auto& kv : dbg) kv.second.first.release();
         if (h_pinned) cudaFreeHost(h_pinned);
         if (hp_pos) cudaFreeHost(hp_pos);

@@ -191,7 +191,8 @@ class _DevPtr:
 
 
 MAX_ATOMS_PER_CALL = 49152        # node-state memory bound of one library call (~100 KB per atom)
-STORE_BYTES_PER_EDGE = 2560 * 4 * 4   # conv outputs kept for the backward: 1408 + 1152 floats = 10.2 KB per edge and layer, 4 layers
+# kept for the backward per edge and layer: conv outputs 1408 + 1152 floats, radial weights 1536, radial pre-activations 2 x 128
+STORE_BYTES_PER_EDGE = (2560 + 1536 + 256) * 4 * 4   # 17.4 KB per edge and layer, 4 layers
 
 
 class UmabEngine:

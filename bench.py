@@ -312,7 +312,7 @@ def main():
             # bf16x3: three bf16 MMAs per fp32-accurate product -> the effective peak is a third
             passes = 3.0 if gemm_name == "tc" else 1.0
             peak = pk["tf_sustained"] / passes
-            roof = {"kernel": "gemm_tc2 (tcgen05 bf16x3, TMA-fed)" if gemm_name == "tc" else "gemm_simt (fp32 FFMA)",
+            roof = {"kernel": "gemm_tc2_pair (tcgen05 cta_group::2 bf16x3, TMA-fed)" if gemm_name == "tc" else "gemm_simt (fp32 FFMA)",
                     "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "peak_source": pk["source"] + f", bf16 dense sustained / {passes:g} passes",
                     "flops_per_launch": d["work"] / max(d["launches"], 1),

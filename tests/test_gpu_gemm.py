@@ -39,11 +39,12 @@ TC2_SHAPES = [s for s in SHAPES if s[2] % 64 == 0 and s[1] % 32 == 0] + [(5, 128
 
 
 @pytest.mark.parametrize("m,n,k", TC2_SHAPES)
-@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("mode", [3, 4, 5, 6])
 @pytest.mark.parametrize("with_bias", [False, True])
 def test_tma_fed_tensor_core_gemm(m, n, k, mode, with_bias, built_lib):
-    """gemm_tc2: both operands by TMA from bf16 hi/lo planes, TMA-store epilogue; k block 64 (mode 3) / 32 (mode 4).
-    Covers row tails (M not a multiple of 128, M < 128) and every N tile width the model uses."""
+    """gemm_tc2: both operands by TMA from bf16 hi/lo planes, TMA-store epilogue; k block 64 (mode 3) / 32 (mode 4);
+    modes 5 / 6 = the CTA-pair (cta_group::2, 256-row tiles) kernel the engine uses by default.
+    Covers row tails (M not a multiple of 128 / 256, M < 128) and every N tile width the model uses."""
     from pdb2reaction_b200 import engine
     g = torch.Generator(device="cuda").manual_seed(m * 5 + n + k)
     a = torch.randn(m, k, device="cuda", generator=g)
@@ -53,3 +54,14 @@ def test_tma_fed_tensor_core_gemm(m, n, k, mode, with_bias, built_lib):
     ref = a.double() @ w.double().T + (b.double() if b is not None else 0.0)
     assert torch.isfinite(c).all()
     assert (c.double() - ref).abs().max() < 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("m,n,k", [(129, 256, 128), (70001, 1024, 512), (8192, 640, 768), (300, 128, 64)])
+def test_cta_pair_gemm_is_bit_identical_to_single_cta(m, n, k, built_lib):
+    """Same MMAs in the same k order per output element: the pair kernel changes which SM holds a tile, not the bits."""
+    from pdb2reaction_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g)
+    assert torch.equal(engine.gemm(a, w, b, mode=3), engine.gemm(a, w, b, mode=5))

@@ -181,12 +181,14 @@ class CudaBackend:
             with torch.cuda.device(dev):
                 _, f = eng.energy_forces(torch.from_numpy(pos[lo:hi]).to(dev), True)
                 torch.cuda.current_stream(dev).synchronize()
-                out[lo:hi].copy_(f)
+                out[lo:hi].copy_(f)                       # device-to-device (peer copy for the other GPUs)
+                torch.cuda.synchronize(dev)
 
         if self._pool is None:
             run(0)
         else:
             list(self._pool.map(run, range(len(self.engines))))
+            torch.cuda.synchronize(self.torch_device)    # peer copies issued from the worker threads have landed
         if self.transform.scale != 1.0:
             out *= float(self.transform.scale)
         return out

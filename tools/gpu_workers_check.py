@@ -16,4 +16,7 @@ r1 = uma_pysis(workers=1).get_forces_batch(elem, c)
 r2 = uma_pysis(workers=2).get_forces_batch(elem, c)
 print("workers=2 equals workers=1:", np.array_equal(r1["energy"], r2["energy"]), np.array_equal(r1["forces"], r2["forces"]))
 h = uma_pysis(workers=2, freeze_atoms=list(range(290))).get_hessian(elem, c[0])["hessian"]
-print("hessian", tuple(h.shape), h.dtype, h.device, float(h.abs().max()))
+h1 = uma_pysis(workers=1, freeze_atoms=list(range(290))).get_hessian(elem, c[0])["hessian"]
+print("hessian", tuple(h.shape), h.dtype, h.device, float(h.abs().max()), "workers=2 equals workers=1:", torch.equal(h, h1.to(h.device)))
+ha = uma_pysis(workers=2, freeze_atoms=list(range(290)), hessian_calc_mode="Analytical").get_hessian(elem, c[0])["hessian"]
+print("analytic vs FD (workers=2): max abs diff", float((ha - h).abs().max()), "of", float(h.abs().max()))

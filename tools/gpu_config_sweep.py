@@ -21,6 +21,7 @@ for name in names:
     dt = (time.perf_counter() - t0) / reps
     eng = calc._core.backend.engines[0]
     # single-image latency (the reference's calling pattern: one image per call)
+    calc.get_forces(elem, c[0])                             # warm-up at the single-image shapes (tensor maps)
     t0 = time.perf_counter()
     for _ in range(3):
         calc.get_forces(elem, c[0])

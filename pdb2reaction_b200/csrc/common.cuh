@@ -53,12 +53,34 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// Blackwell packed fp32 (FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, same results as the scalar
+// forms) halves the issue slots of the Wigner rotations in the latency-bound edge kernels.  UMAB_NO_F32X2 restores scalars.
+#if !defined(UMAB_NO_F32X2)
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) {
+    const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+#else
 __device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+#endif
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ void f4fma(float4& acc, float s, float4 b) {
+#if !defined(UMAB_NO_F32X2)
+    const float2 s2 = make_float2(s, s);
+    const float2 lo = __ffma2_rn(s2, make_float2(b.x, b.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(s2, make_float2(b.z, b.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+#else
     acc.x = fmaf(s, b.x, acc.x); acc.y = fmaf(s, b.y, acc.y); acc.z = fmaf(s, b.z, acc.z); acc.w = fmaf(s, b.w, acc.w);
+#endif
 }
 __device__ __forceinline__ float f4dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ float f4hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }

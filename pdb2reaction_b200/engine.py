@@ -16,7 +16,8 @@ import torch
 
 from .arch import UMAArch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
+# UMAB_LIB: load another build of the same library (A/B measurements of compile-time kernel variants)
+_LIB_PATH = os.environ.get("UMAB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
 ABI_VERSION = 6

@@ -44,6 +44,10 @@ def parse():
     p.add_argument("--experts", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-atoms", type=int, default=None)
+    p.add_argument("--hessian", action="store_true",
+                   help="measure BASELINE.json's second metric instead: wall time of the full FD Hessian of the C3 "
+                        "cluster (--hessian-atoms), column blocks sharded over the N ranks, one all_gather")
+    p.add_argument("--hessian-atoms", type=int, default=500)
     return p.parse_args()
 
 
@@ -193,6 +197,67 @@ def emit(obj):
         sys.stdout.flush()
 
 
+def run_hessian(args, world, rank, local):
+    """Hessian wall-time (BASELINE.json metric, configs[2]): full FiniteDifference Hessian (1 + 2*3N force evaluations,
+    reference uma_pysis.py:595-686) of an N-atom cluster through the public calculator; with N ranks the active
+    columns shard over the ranks and ONE all_gather of the column blocks follows (sharding.sharded_fd_hessian).
+    A "step" = one full Hessian, coordinates on the host, result a device tensor + D2H of its norm."""
+    import warnings
+    import torch.distributed as dist
+    from pdb2reaction_b200 import synth, uma_pysis
+    from pdb2reaction_b200.shims import ANG2BOHR
+    from pdb2reaction_b200.sharding import sharded_fd_hessian
+    n = args.hessian_atoms
+    elem, coords = synth.make_cluster(n, 3)
+    c = (coords * ANG2BOHR).reshape(-1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        calc = uma_pysis(device=f"cuda:{local}")
+        calc.get_forces(elem, c)                                  # engine build + warm-up
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    steps = max(1, min(args.steps, 2))
+    eng = calc._core.backend.engines[0]
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = sharded_fd_hessian(calc, elem, c)
+        hnorm = float(r["hessian"].abs().max())                   # D2H read of the result
+    barrier()
+    dt = (time.perf_counter() - t0) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats()["kernel_launches"] - launches0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = t.item()
+    if rank == 0:
+        h = r["hessian"]
+        emit({"metric": "Hessian wall-time", "value": dt, "unit": "s", "n_gpus": world, "steps": steps, "warmup": 1,
+              "ms_per_step": 1e3 * dt, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+              "dtype": "f32 forces (bf16x3 split tensor-core GEMMs), f64 Hessian assembly", "data": "synthetic",
+              "config": {"workload": f"C3: full FiniteDifference Hessian of a {n}-atom cluster (BASELINE.json configs[2]), "
+                                     f"{3 * n} columns = {1 + 6 * n} force evaluations, column blocks sharded over {world} GPU(s)",
+                         "n_atoms": n, "columns": 3 * n, "collective": "none (1 GPU)" if world == 1 else "one all_gather of the column blocks"},
+              "columns_per_s": 3 * n / dt, "force_evals_per_s": (1 + 6 * n) / dt,
+              "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int((1 + 6 * n) * n * 12 // world),
+                      "d2h_bytes_per_step": 8, "api": "sharding.sharded_fd_hessian(uma_pysis, elem, coords_bohr) "
+                      "(= uma_pysis.get_hessian at N = 1): host coordinates in, Hessian on the device + one scalar read back"},
+              "gpu_launches": int(launches), "clocks": clocks,
+              "hessian": {"shape": list(h.shape), "dtype": str(h.dtype), "max_abs": hnorm,
+                          "asym": float((h - h.T).abs().max())}})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
@@ -210,6 +275,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.hessian:
+        return run_hessian(args, world, rank, local)
 
     from pdb2reaction_b200 import calculator as calc_mod
     from pdb2reaction_b200 import engine as engine_mod

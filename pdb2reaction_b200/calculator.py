@@ -338,22 +338,21 @@ class uma_pysis(Calculator):
         return (c.reshape(-1, n, 3) if batch else c.reshape(-1, 3)) * BOHR2ANG
 
     # ---------- finite-difference Hessian, batched (reference :595-686) ---------------
-    def _build_fd_hessian(self, coord_ang: np.ndarray, eps_ang: float = FD_STEP_ANG):
+    def _fd_columns_into(self, hmat: torch.Tensor, coord_ang: np.ndarray, dofs: Sequence[int],
+                         eps_ang: float = FD_STEP_ANG) -> None:
+        """hmat[:, k] = -(F(x + h e_k) - F(x - h e_k)) / 2h for k in ``dofs`` (reference :652-675), the displaced
+        geometries evaluated as batches; any subset of columns (column blocks shard over ranks, sharding.py)."""
         core = self._core
-        dev = core.device
+        dev = hmat.device
         n_atoms = coord_ang.shape[0]
         dof = 3 * n_atoms
-        active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
-        res0 = core.compute(coord_ang, forces=True)
-        f0 = res0["forces"]
-        hdt = torch.float64 if self.hessian_double else torch.float32
-        hmat = torch.zeros((dof, dof), device=dev, dtype=hdt)
+        dofs = [int(k) for k in dofs]
         # all +h / -h geometries, displaced in float64 before the fp32 cast (Q3)
         per = max(1, MAX_ATOMS_PER_CALL // n_atoms) * len(getattr(core.backend, "engines", [0]))
         per = max(2, per - per % 2)
         on_device = hasattr(core.backend, "forces_device")        # CUDA backend: the columns never visit the host
-        for s in range(0, len(active_dof), per // 2):
-            ks = active_dof[s:s + per // 2]
+        for s in range(0, len(dofs), per // 2):
+            ks = dofs[s:s + per // 2]
             batch = np.repeat(coord_ang[None], 2 * len(ks), axis=0)
             for q, k in enumerate(ks):
                 a, c = divmod(k, 3)
@@ -365,17 +364,30 @@ class uma_pysis(Calculator):
                                     torch.as_tensor(ks, device=dev, dtype=torch.int32), eps_ang)
                 continue
             f = core.compute_batch(batch, forces=True)["forces"].reshape(2 * len(ks), dof)
-            ft = torch.from_numpy(f).to(dev, dtype=hdt)
+            ft = torch.from_numpy(f).to(dev, dtype=hmat.dtype)
             cols = -(ft[0::2] - ft[1::2]) / (2.0 * eps_ang)                 # [len(ks), dof]
             hmat[:, torch.as_tensor(ks, device=dev, dtype=torch.long)] = cols.T
+
+    def _finish_fd_hessian(self, hmat: torch.Tensor, n_atoms: int):
+        """Active-block reduction / (N,3,N,3) view of the assembled [dof, dof] matrix (reference :678-684)."""
+        active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
         if self.return_partial_hessian:
-            idx = torch.as_tensor(active_dof, device=dev, dtype=torch.long)
+            idx = torch.as_tensor(active_dof, device=hmat.device, dtype=torch.long)
             hmat = hmat.index_select(0, idx).index_select(1, idx)
             na = len(active_atoms)
-            hmat = hmat.view(na, 3, na, 3)
-        else:
-            hmat = hmat.view(n_atoms, 3, n_atoms, 3)
-        return {"energy": res0["energy"], "forces": f0, "hessian": hmat}
+            return hmat.view(na, 3, na, 3)
+        return hmat.view(n_atoms, 3, n_atoms, 3)
+
+    def _build_fd_hessian(self, coord_ang: np.ndarray, eps_ang: float = FD_STEP_ANG):
+        core = self._core
+        n_atoms = coord_ang.shape[0]
+        dof = 3 * n_atoms
+        _, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
+        res0 = core.compute(coord_ang, forces=True)
+        hdt = torch.float64 if self.hessian_double else torch.float32
+        hmat = torch.zeros((dof, dof), device=core.device, dtype=hdt)
+        self._fd_columns_into(hmat, coord_ang, active_dof, eps_ang)
+        return {"energy": res0["energy"], "forces": res0["forces"], "hessian": self._finish_fd_hessian(hmat, n_atoms)}
 
     # ---------- analytic Hessian: dual-number columns (reference :394-415, :569-592) ----
     def _build_analytic_hessian(self, coord_ang: np.ndarray):

@@ -8,7 +8,11 @@ lives on rank 0) sees the whole string -- the new meaning of the reference's ``w
 (``pdb2reaction/uma_pysis.py:52-63, 213-242``; there: Ray actors + graph parallelism over ONE
 structure).
 
-Two drivers use this module:
+Hessian column blocks shard the same way (BASELINE.json configs[2]): ``sharded_fd_hessian`` gives every rank a
+contiguous block of the active columns and ends in ONE all_gather of the blocks.
+
+Three drivers use this module:
+* ``sharded_fd_hessian``: one process per GPU under ``torchrun`` (bench.py ``--hessian --gpus N``);
 * ``CudaBackend`` (calculator.py): one process, one host thread per GPU, no collective at all;
 * ``SpmdEvaluator``: one process per GPU under ``torchrun`` (bench.py ``--gpus N``), NCCL
   all-gather over NVLink (gloo on CPU in the tests).
@@ -82,3 +86,42 @@ class SpmdEvaluator:
             es.append(er)
             fs.append(fr)
         return torch.cat(es), torch.cat(fs)
+
+
+
+def sharded_fd_hessian(calc, elem, coords_bohr, group: Optional[dist.ProcessGroup] = None):
+    """``calc.get_hessian(elem, coords)`` in FiniteDifference mode with the ACTIVE COLUMNS sharded over the ranks of
+    ``group`` (one process per GPU): rank r evaluates the +-h displacements of its contiguous block of active degrees
+    of freedom on its own device, then one all_gather of the column blocks (``[cols_r, 3N]`` each; C3: 9 MB fp32 /
+    18 MB fp64 in total) gives every rank the full matrix, which goes through the calculator's own symmetrise / unit /
+    dtype formatting (reference ``uma_pysis.py:515-551``).  Same result bits as the single-process path."""
+    from .calculator import FD_STEP_ANG
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    calc._ensure_core(elem)
+    coord_ang = calc._coords_ang(coords_bohr)
+    core = calc._core
+    n_atoms = coord_ang.shape[0]
+    dof = 3 * n_atoms
+    _, active_dof, _ = calc._active_and_frozen_dof_idx(n_atoms)
+    res0 = core.compute(coord_ang, forces=True)
+    hdt = torch.float64 if calc.hessian_double else torch.float32
+    hmat = torch.zeros((dof, dof), device=core.device, dtype=hdt)
+    bounds = shard_bounds(len(active_dof), world)
+    lo, hi = bounds[rank]
+    calc._fd_columns_into(hmat, coord_ang, active_dof[lo:hi], FD_STEP_ANG)
+    if world > 1:
+        cap = max(h - l for l, h in bounds)
+        mine = torch.zeros((cap, dof), device=hmat.device, dtype=hdt)
+        if hi > lo:
+            idx = torch.as_tensor(active_dof[lo:hi], device=hmat.device, dtype=torch.long)
+            mine[: hi - lo] = hmat.index_select(1, idx).T
+        blocks = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(blocks, mine, group=group)          # the ONE collective of a Hessian
+        for r, (l, h) in enumerate(bounds):
+            if h > l and r != rank:
+                idx = torch.as_tensor(active_dof[l:h], device=hmat.device, dtype=torch.long)
+                hmat[:, idx] = blocks[r][: h - l].T
+    f_ev = calc._zero_frozen_forces_ev(res0["forces"])
+    return {"energy": calc._au_energy(res0["energy"]), "forces": calc._au_forces(f_ev),
+            "hessian": calc._au_hessian(calc._finish_fd_hessian(hmat, n_atoms))}

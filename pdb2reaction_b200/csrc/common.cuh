@@ -37,7 +37,8 @@ inline void check_cuda(cudaError_t e, const char* what, const char* file, int li
 extern std::atomic<long long> g_launch_count;   // kernels launched by this library (defined in engine.cu)
 #define UMAB_LAUNCH_CHECK() (++::umab::g_launch_count, ::umab::check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__))
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// denominator in [1, inf): the fast reciprocal (MUFU.RCP, <= 2 ulp) needs none of the IEEE division's range fix-ups
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float dsiluf_(float x) {
     float s = sigmoidf_(x);
@@ -91,14 +92,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the operand format of the bf16x3 tensor-core GEMMs
 __device__ __forceinline__ void split4(float4 x, uint2& hi, uint2& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
-                        h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
-    __nv_bfloat162 ha, hb;
-    ha.x = h0; ha.y = h1; hb.x = h2; hb.y = h3;
-    hi.x = *reinterpret_cast<uint32_t*>(&ha);
-    hi.y = *reinterpret_cast<uint32_t*>(&hb);
-    lo.x = pack_bf16(x.x - __bfloat162float(h0), x.y - __bfloat162float(h1));
-    lo.y = pack_bf16(x.z - __bfloat162float(h2), x.w - __bfloat162float(h3));
+    // packed conversions (F2FP.BF16.F32.PACK_AB: two floats -> one bf16x2 register) and bit-level widening of hi
+    hi.x = pack_bf16(x.x, x.y);
+    hi.y = pack_bf16(x.z, x.w);
+    const float h0 = __uint_as_float(hi.x << 16), h1 = __uint_as_float(hi.x & 0xffff0000u);
+    const float h2 = __uint_as_float(hi.y << 16), h3 = __uint_as_float(hi.y & 0xffff0000u);
+    lo.x = pack_bf16(x.x - h0, x.y - h1);
+    lo.y = pack_bf16(x.z - h2, x.w - h3);
 }
 
 // ---------------------------------------------------------------- GEMM (C = A W^T [+bias] [+C])

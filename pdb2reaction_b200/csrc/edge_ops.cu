@@ -390,8 +390,8 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 //   HALF = 1  one warp per target node i, over its in-edges  (CSR row):       g_x[i]  = sum of target-half terms
 //   HALF = 0  one warp per source node j, over its out-edges (sedge list):    g_x[j] += sum of source-half terms
 // Both add their share of dL/dD into g_wig[e]; HALF = 1 runs first, HALF = 0 second (fixed order: deterministic).
-template <int HALF, class S, int MINB>
-__global__ void __launch_bounds__(256, min_blocks<S>(MINB))
+template <int HALF, class S>
+__global__ void __launch_bounds__(256)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
                               GP<S> g_x, GP<S> g_wig) {
@@ -716,22 +716,13 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
                                        long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
                                        GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
-    // UMAB_HALF_OCC=2: 128-register build (2 CTAs per SM, some spills) for A/B measurements
-    static const bool occ2 = [] { const char* e = getenv("UMAB_HALF_OCC"); return e && atoi(e) == 2; }();
+    // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
     const dim3 grid((n_nodes + 7) / 8);
-    if (occ2) {
-        gather_rotate_bwd_half_kernel<1, S, 2><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1,
-                                                                    gA2, g_rad, g_x, g_wig);
-        UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, 2><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
-                                                                    g_rad, g_x, g_wig);
-    } else {
-        gather_rotate_bwd_half_kernel<1, S, 1><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1,
-                                                                    gA2, g_rad, g_x, g_wig);
-        UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, 1><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
-                                                                    g_rad, g_x, g_wig);
-    }
+    gather_rotate_bwd_half_kernel<1, S><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
+                                                             g_rad, g_x, g_wig);
+    UMAB_LAUNCH_CHECK();
+    gather_rotate_bwd_half_kernel<0, S><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2, g_rad,
+                                                             g_x, g_wig);
     UMAB_LAUNCH_CHECK();
 }
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st) {

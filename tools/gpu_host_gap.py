@@ -11,7 +11,8 @@ arch = UMAArch()
 elem, imgs = synth.make_string(1500, 32, 4)
 z = atomic_numbers(elem)
 merged = W.merge_mole(W.init_uma_weights(arch, seed=0), arch, z, 0, 1, "omol")
-eng = UmabEngine(merged, z, arch)
+store = int(float(os.environ.get("STORE_GB", "0")) * 1e9)
+eng = UmabEngine(merged, z, arch, store_bytes=store)
 pos = torch.from_numpy(imgs.astype(np.float32)).cuda()
 for _ in range(3):
     eng.energy_forces(pos)
@@ -19,7 +20,7 @@ torch.cuda.synchronize()
 import pynvml
 pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)
-for it in range(12):
+for it in range(6):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()

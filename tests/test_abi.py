@@ -65,3 +65,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+
+
+def test_header_is_plain_c_and_links_against_the_library(built_lib, tmp_path):
+    """include/umab.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in the signatures) and a C
+    program must link against libumab.so and read the ABI version (no compute call: there is no GPU here)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "umab.h"\n#include <stdio.h>\n'
+                   'int main(void){ printf("%d %d\\n", (int)umab_abi_version(), (int)UMAB_ABI_VERSION);\n'
+                   ' return umab_abi_version() == UMAB_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    libdir = os.path.dirname(built_lib)
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{inc}", str(src), "-o", str(exe),
+                        f"-L{libdir}", "-lumab", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and len(set(r.stdout.split())) == 1, (r.stdout, r.stderr)

@@ -429,7 +429,7 @@ struct umab_engine {
     }
 
     template <class S> void plan_chunks() {
-        long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (24LL << 30);
+        long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (28LL << 30);   // one 10k-atom image (~0.8 M edges) stays a closed chunk
         const bool extra = want_adjoint && !store_mode;
         const size_t per_edge = EDGE_WS_FLOATS + (extra ? EDGE_WS_EXTRA_RECOMPUTE : 0);
         long long cap = std::max<long long>(budget / (long long)(per_edge * 4 * planes<S>()), 1024);

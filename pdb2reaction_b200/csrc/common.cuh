@@ -37,32 +37,6 @@ inline void check_cuda(cudaError_t e, const char* what, const char* file, int li
 extern std::atomic<long long> g_launch_count;   // kernels launched by this library (defined in engine.cu)
 #define UMAB_LAUNCH_CHECK() (++::umab::g_launch_count, ::umab::check_cuda(cudaGetLastError(), "kernel launch", __FILE__, __LINE__))
 
-// ---- programmatic dependent launch (PDL): kernels that begin with pdl_sync() may be LAUNCHED while the preceding kernel
-// of the stream drains its last wave (CTA scheduling, prologue, TMEM allocation overlap that tail); griddepcontrol.wait
-// then blocks until the predecessor has completed and flushed its memory, so every global access stays ordered.
-// launch_k() sets the launch attribute when UMAB_PDL=1; a kernel launched through it MUST call pdl_sync() (or
-// pdl_trigger() + pdl_wait()) before it touches global memory.
-#ifdef __CUDACC__
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
-inline bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("UMAB_PDL"); return e && atoi(e) == 1; }();
-    return on;
-}
-template <class... KArgs, class... Args>
-inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    ++g_launch_count;
-    check_cuda(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...), "kernel launch", __FILE__, __LINE__);
-}
-#endif
-
 // denominator in [1, inf): the fast reciprocal (MUFU.RCP, <= 2 ulp) needs none of the IEEE division's range fix-ups
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }

@@ -202,7 +202,6 @@ template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
                            long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -269,7 +268,6 @@ template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 gather_rotate_scale_wide_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
                                 long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -305,7 +303,6 @@ __global__ void __launch_bounds__(256)
 gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __restrict__ src, GP<S> wig, GP<S> rad,
                          long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                          GP<S> g_x, GP<S> g_wig) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int nl = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -398,7 +395,6 @@ __global__ void __launch_bounds__(256)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
                               GP<S> g_x, GP<S> g_wig) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int nl = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -472,7 +468,6 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
 __global__ void __launch_bounds__(256)
 source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, const int* __restrict__ sedge,
                      int n_nodes, float* __restrict__ g_x) {
-    pdl_sync();
     const int j = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (j >= n_nodes) return;
@@ -493,7 +488,6 @@ source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, 
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(4))
 combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -524,7 +518,6 @@ template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
 combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0, AP<S> gY1,
                         AP<S> gY2) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -615,7 +608,6 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
     for (int r = 0; r < 9; ++r) acc[r] = vzero<V>();
     const long long e_end = row_ptr[i + 1];
     for (long long e = row_ptr[i]; e < e_end; ++e) {
-    pdl_sync();
         if (e + 1 < e_end) {
             const long long en = e + 1 - e0;
             if (lane < 9) wig.prefetch((e + 1) * WIG + lane * 4);
@@ -651,7 +643,6 @@ template <int MODE, class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
                        long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int el = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -706,16 +697,18 @@ void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S>
                                   AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st) {
     if (n_e <= 0) return;
     static const bool wide = [] { const char* e = getenv("UMAB_GRS_VARIANT"); return e && atoi(e) == 1; }();
-    if (wide) launch_k(gather_rotate_scale_wide_kernel<S>, (n_e + 7) / 8, 256, 0, st, x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
-    else launch_k(gather_rotate_scale_kernel<S>, (n_e + 7) / 8, 256, 0, st, x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    if (wide) gather_rotate_scale_wide_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    else gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<S> wig, GP<S> rad, long long e0,
                                 int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                                 GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
-    launch_k(gather_rotate_bwd_kernel<S>, (n_nodes + 7) / 8, 256, 0, st, x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
+    gather_rotate_bwd_kernel<S><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
                                                                    gA1, gA2, g_rad, G, g_x, g_wig);
+    UMAB_LAUNCH_CHECK();
 }
 // closed chunks: target halves over the CSR rows, then source halves over the out-edge lists (no G, no source_reduce)
 template <class S>
@@ -725,25 +718,30 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
     if (n_nodes <= 0) return;
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
     const dim3 grid((n_nodes + 7) / 8);
-    launch_k(gather_rotate_bwd_half_kernel<1, S>, grid, 256, 0, st, x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
+    gather_rotate_bwd_half_kernel<1, S><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
                                                              g_rad, g_x, g_wig);
-    launch_k(gather_rotate_bwd_half_kernel<0, S>, grid, 256, 0, st, x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2, g_rad,
+    UMAB_LAUNCH_CHECK();
+    gather_rotate_bwd_half_kernel<0, S><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2, g_rad,
                                                              g_x, g_wig);
+    UMAB_LAUNCH_CHECK();
 }
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st) {
     if (n_nodes <= 0) return;
-    launch_k(source_reduce_kernel, (n_nodes + 7) / 8, 256, 0, st, G, sptr, sedge, n_nodes, g_x);
+    source_reduce_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(G, sptr, sedge, n_nodes, g_x);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st) {
     if (n_e <= 0) return;
-    launch_k(combine_gate_fwd_kernel<S>, (n_e + 7) / 8, 256, 0, st, Y0, Y1, Y2, n_e, B0, B1, B2);
+    combine_gate_fwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
                                AP<S> gY1, AP<S> gY2, cudaStream_t st) {
     if (n_e <= 0) return;
-    launch_k(combine_gate_bwd_kernel<S>, (n_e + 7) / 8, 256, 0, st, Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
+    combine_gate_bwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* row_ptr, GP<S> wig, GP<S> env,
@@ -752,9 +750,10 @@ void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const i
     if (n_nodes <= 0) return;
     dim3 grid((n_nodes + 7) / 8);
     if (mode == 0)
-        launch_k(rotate_back_reduce_kernel<0, S>, grid, 256, 0, st, Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
     else
-        launch_k(rotate_back_reduce_kernel<1, S>, grid, 256, 0, st, Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* tgt, GP<S> wig, GP<S> env, float scale,
@@ -763,9 +762,10 @@ void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int*
     if (n_e <= 0) return;
     dim3 grid((n_e + 7) / 8);
     if (mode == 0)
-        launch_k(rotate_back_bwd_kernel<0, S>, grid, 256, 0, st, Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+        rotate_back_bwd_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
     else
-        launch_k(rotate_back_bwd_kernel<1, S>, grid, 256, 0, st, Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+        rotate_back_bwd_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+    UMAB_LAUNCH_CHECK();
 }
 
 #define UMAB_INST(S)                                                                                                  \

@@ -44,7 +44,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
                 const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                 const __grid_constant__ CUtensorMap tm_c, Tc2Params p) {
-    pdl_trigger();                     // the next kernel of the stream may start scheduling while this one drains
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int ROW_BYTES = BK * 2;
     constexpr uint32_t A_PLANE = BM * ROW_BYTES;
@@ -85,7 +84,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
-    pdl_wait();                        // barriers / TMEM are set up; from here on global memory of the predecessor is read
 
     if (warp == 0) {
         // ===================== TMA producer: one elected lane streams the four operand tiles of every k block
@@ -212,7 +210,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant__ CUtensorMap tm_al,
                      const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
                      const __grid_constant__ CUtensorMap tm_c, Tc2Params p) {
-    pdl_trigger();                     // the next kernel of the stream may start scheduling while this one drains
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int ROW_BYTES = BK * 2;
     constexpr uint32_t A_PLANE = BM * ROW_BYTES;
@@ -257,7 +254,6 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_con
     cluster_sync_all();                    // both CTAs' barriers are initialised before any remote arrive / TMA complete_tx
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
-    pdl_wait();                        // barriers / TMEM are set up; from here on global memory of the predecessor is read
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs): own A rows, own half of the W tile; bytes land on the leader's barrier
@@ -517,7 +513,8 @@ void launch_tc2(const CUtensorMap& ah, const CUtensorMap& al, const Planes2& pl,
     std::call_once(attr_once[dev & 15], [] {
         UMAB_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     });
-    launch_k(gemm_tc2_kernel<BK>, grid, T2_THREADS, smem, st, ah, al, pl.tm_hi, pl.tm_lo, cm, p);
+    gemm_tc2_kernel<BK><<<grid, T2_THREADS, smem, st>>>(ah, al, pl.tm_hi, pl.tm_lo, cm, p);
+    UMAB_LAUNCH_CHECK();
 }
 
 // CTAs of the pair kernel that can be resident at once (2 x the co-resident clusters; 0 = cluster launch unsupported)
@@ -550,7 +547,8 @@ void launch_tc2_pair(const CUtensorMap& ah, const CUtensorMap& al, const Planes2
     const int cap = pair_max_ctas<BK>(dev);
     if (cap < 2) throw CudaError("gemm_tc2: the CTA-pair kernel cannot be launched on this device");
     dim3 grid((unsigned)std::min<long long>(2 * pair_tiles, cap));
-    launch_k(gemm_tc2_pair_kernel<BK>, grid, T2_THREADS, smem, st, ah, al, pl.tm_hi_half, pl.tm_lo_half, cm, p);
+    gemm_tc2_pair_kernel<BK><<<grid, T2_THREADS, smem, st>>>(ah, al, pl.tm_hi_half, pl.tm_lo_half, cm, p);
+    UMAB_LAUNCH_CHECK();
 }
 
 }  // namespace

@@ -20,7 +20,6 @@ __global__ void __launch_bounds__(256)
 ln_silu_fwd_kernel(GP<S> u, AP<S> h, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ bias, const float* __restrict__ t_src, const float* __restrict__ t_tgt,
                    const int* __restrict__ z, const int* __restrict__ src, const int* __restrict__ tgt, int rows) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int row = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -57,7 +56,6 @@ ln_silu_fwd_kernel(GP<S> u, AP<S> h, const float* __restrict__ gamma, const floa
 template <class S>
 __global__ void __launch_bounds__(256)
 ln_silu_bwd_kernel(GP<S> u, GP<S> g, AP<S> out, const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
-    pdl_sync();
     using V = typename VecOf<S>::type;
     const int row = blockIdx.x * 8 + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
@@ -97,12 +95,14 @@ void launch_ln_silu_fwd_t(GP<S> u, AP<S> h, const float* gamma, const float* bet
                           const float* t_src, const float* t_tgt, const int* z, const int* src, const int* tgt,
                           int rows, cudaStream_t st) {
     if (rows <= 0) return;
-    launch_k(ln_silu_fwd_kernel<S>, (rows + 7) / 8, 256, 0, st, u, h, gamma, beta, bias, t_src, t_tgt, z, src, tgt, rows);
+    ln_silu_fwd_kernel<S><<<(rows + 7) / 8, 256, 0, st>>>(u, h, gamma, beta, bias, t_src, t_tgt, z, src, tgt, rows);
+    UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st) {
     if (rows <= 0) return;
-    launch_k(ln_silu_bwd_kernel<S>, (rows + 7) / 8, 256, 0, st, u, g, out, gamma, beta, rows);
+    ln_silu_bwd_kernel<S><<<(rows + 7) / 8, 256, 0, st>>>(u, g, out, gamma, beta, rows);
+    UMAB_LAUNCH_CHECK();
 }
 template void launch_ln_silu_fwd_t<float>(GP<float>, AP<float>, const float*, const float*, const float*, const float*,
                                           const float*, const int*, const int*, const int*, int, cudaStream_t);

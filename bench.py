@@ -232,7 +232,7 @@ def run_hessian(args, world, rank, local):
     c = (coords * ANG2BOHR).reshape(-1)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        calc = uma_pysis(device=f"cuda:{local}")
+        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}")
         calc.get_forces(elem, c)                                  # engine build + warm-up
 
     def barrier():
@@ -315,7 +315,7 @@ def main():
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        calc = uma_pysis(device=f"cuda:{local}")       # the public API object (e2e path)
+        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}")       # the public API object (e2e path)
         calc._ensure_core(elem)
     eng = calc._core.backend.engines[0]
     pos_dev = torch.from_numpy(imgs.astype(np.float32)).cuda()

@@ -20,6 +20,7 @@ from __future__ import annotations
 import os
 import threading
 import warnings
+from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -56,6 +57,7 @@ CALC_KW: Dict[str, Any] = {
     "hessian_double": True,
 }
 
+RANDOM_PREFIX = "random:"      # model="random:<id>": random-init weights of that architecture (tests / benches)
 FD_STEP_ANG = 1.0e-3            # reference uma_pysis.py:600
 MAX_ATOMS_PER_CALL = 49152      # FD-Hessian batching unit (the engine sub-batches further if needed)
 
@@ -65,7 +67,31 @@ MAX_ATOMS_PER_CALL = 49152      # FD-Hessian batching unit (the engine sub-batch
 # ======================================================================================
 _state_lock = threading.Lock()
 _state_cache: Dict[str, tuple] = {}
-_engine_cache: Dict[tuple, Any] = {}
+# engines by (weights, composition, charge, spin, task, graph options, arch, device), least recently used first.
+# An engine owns GBs of workspace: the cache keeps at most ENGINE_CACHE_MAX of them alive; an evicted engine is
+# only dropped from the cache -- calculators still holding it keep working, and its memory is released when the
+# last of them goes away (UmabEngine.__del__).
+_engine_cache: "OrderedDict[tuple, Any]" = OrderedDict()
+ENGINE_CACHE_MAX = max(1, int(os.environ.get("UMAB_ENGINE_CACHE", "4")))
+
+
+def _engine_cache_get(key):
+    with _state_lock:
+        eng = _engine_cache.get(key)
+        if eng is not None:
+            _engine_cache.move_to_end(key)
+        return eng
+
+
+def _engine_cache_put(key, eng, n_devices: int = 1):
+    with _state_lock:
+        _engine_cache[key] = eng
+        _engine_cache.move_to_end(key)
+        per_dev: Dict[int, int] = {}
+        for k in reversed(list(_engine_cache)):           # newest first; keep ENGINE_CACHE_MAX per device
+            per_dev[k[-1]] = per_dev.get(k[-1], 0) + 1
+            if per_dev[k[-1]] > ENGINE_CACHE_MAX:
+                del _engine_cache[k]
 
 
 def load_model_state(model: str, arch: UMAArch, task_name: str = "omol"):
@@ -74,22 +100,27 @@ def load_model_state(model: str, arch: UMAArch, task_name: str = "omol"):
     ``model`` is either a path -- a fairchem ``MLIPInferenceCheckpoint`` / fairchem-named state dict
     (converted by ``checkpoint.load_checkpoint``, no fairchem install needed) or a ``torch.save``d state
     dict in this package's naming (``weights.init_uma_weights``) -- or a model ID such as
-    ``"uma-s-1p1"``.  The reference downloads the ID from a gated HF repo (``uma_pysis.py:246-250``);
-    offline that is impossible, so an ID resolves to ``$UMAB_WEIGHTS`` if set, else to RANDOM-INIT
-    weights of the uma-s-1p1 architecture (seed 0) with a warning -- energies are then not physical.
+    ``"uma-s-1p1"``.  The reference downloads the ID from a gated HF repo (``uma_pysis.py:246-250``) and
+    fails hard when it cannot; here an ID resolves to ``$UMAB_WEIGHTS`` if set and otherwise RAISES.
+    Random-init weights of the uma-s-1p1 architecture (seed 0; energies are then not physical) are an
+    explicit opt-in for tests and benches: ``model="random:uma-s-1p1"`` or ``UMAB_ALLOW_RANDOM_WEIGHTS=1``.
     """
     from .checkpoint import EnergyTransform, load_checkpoint
-    path = model if os.path.exists(str(model)) else os.environ.get("UMAB_WEIGHTS")
+    model = str(model)
+    explicit_random = model.startswith(RANDOM_PREFIX)
+    path = None if explicit_random else (model if os.path.exists(model) else os.environ.get("UMAB_WEIGHTS"))
     key = f"file:{path}:{task_name}" if path else f"random:{model}:{arch.num_experts}"
     with _state_lock:
         if key not in _state_cache:
             if path:
                 _state_cache[key] = load_checkpoint(path, arch, task_name=task_name)
-            else:
-                warnings.warn(
-                    f"no checkpoint available for model {model!r} (offline): using random-init "
-                    "uma-s-1p1-architecture weights, seed 0", RuntimeWarning, stacklevel=3)
+            elif explicit_random or os.environ.get("UMAB_ALLOW_RANDOM_WEIGHTS", "0") not in ("", "0"):
                 _state_cache[key] = (_weights.init_uma_weights(arch, seed=0), EnergyTransform())
+            else:
+                raise FileNotFoundError(
+                    f"no checkpoint for model {model!r}: pass a checkpoint path as `model`, or set $UMAB_WEIGHTS "
+                    "(there is no network download).  Random-init weights of the same architecture are available "
+                    f"only on request: model='{RANDOM_PREFIX}{model}' or UMAB_ALLOW_RANDOM_WEIGHTS=1")
         return _state_cache[key]
 
 
@@ -117,22 +148,23 @@ class CudaBackend:
             raise RuntimeError(f"workers={workers} requested from cuda:{first} but only {n_gpu} GPUs are visible")
         self.devices = list(range(first, first + workers))
         self.torch_device = torch.device("cuda", first)
-        key_base = (str(model), tuple(self.z), int(charge), int(spin), str(task_name),
-                    None if radius is None else float(radius), None if max_neigh is None else int(max_neigh))
+        weights_id = str(model) if (str(model).startswith(RANDOM_PREFIX) or os.path.exists(str(model))) \
+            else f"{model}|{os.environ.get('UMAB_WEIGHTS', '')}"
+        key_base = (weights_id, tuple(self.z), int(charge), int(spin), str(task_name),
+                    None if radius is None else float(radius), None if max_neigh is None else int(max_neigh),
+                    repr(self.arch))
         self.engines = []
         # normaliser + element references of the prediction unit; identity for random-init
         _, self.transform = load_model_state(model, self.arch, task_name)
         self._e_const = self.transform.constant_for(self.z)
         for d in self.devices:
             key = key_base + (d,)
-            with _state_lock:
-                eng = _engine_cache.get(key)
+            eng = _engine_cache_get(key)
             if eng is None:
                 state, _ = load_model_state(model, self.arch, task_name)
                 merged = _weights.merge_mole(state, self.arch, self.z, charge, spin, task_name)
                 eng = UmabEngine(merged, self.z, self.arch, device=d, cutoff=radius, max_neighbors=max_neigh)
-                with _state_lock:
-                    _engine_cache[key] = eng
+                _engine_cache_put(key, eng)
             self.engines.append(eng)
         self._pool = ThreadPoolExecutor(max_workers=len(self.engines)) if len(self.engines) > 1 else None
 
@@ -441,6 +473,8 @@ class uma_pysis(Calculator):
         try:
             res = self._build_analytic_hessian(coord_ang) if analytic else self._build_fd_hessian(coord_ang)
         except torch.cuda.OutOfMemoryError as e:
+            if not analytic:
+                raise                # the reference's FD path lets the allocator's error through (uma_pysis.py:768)
             raise RuntimeError(
                 "Analytical Hessian computation failed due to CUDA out-of-memory. "
                 "Your GPU memory appears to be limited. Please switch to the finite-"

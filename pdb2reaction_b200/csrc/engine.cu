@@ -48,7 +48,7 @@ thread_local std::string g_last_error;
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-    static long long total;
+    static std::atomic<long long> total;       // engines on several GPUs allocate from their own host threads
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
         if (p) { cudaFree(p); total -= (long long)cap; }
@@ -74,7 +74,7 @@ struct DevBuf {
     float* f() const { return reinterpret_cast<float*>(p); }
     int* i() const { return reinterpret_cast<int*>(p); }
 };
-long long DevBuf::total = 0;
+std::atomic<long long> DevBuf::total{0};
 
 // a tensor of the pipeline: value plane + (Hessian path only) tangent plane
 struct TBuf {
@@ -1078,7 +1078,7 @@ int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_byt
     UMAB_TRY
     (void)e;
     if (kernel_launches) *kernel_launches = g_launch_count.load();
-    if (device_bytes) *device_bytes = DevBuf::total;
+    if (device_bytes) *device_bytes = DevBuf::total.load();
     UMAB_CATCH
 }
 

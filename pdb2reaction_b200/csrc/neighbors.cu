@@ -17,6 +17,8 @@
 //    atoms and emitted by scanning the bitmap, so the row is sorted by source whatever the order inside
 //    the cells (which comes from integer atomics) -- same canonical (target, source) order, no sort.
 // Both: two passes (count, fill) around a prefix sum.
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace umab {
@@ -453,10 +455,18 @@ void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float c
                                const int* row_ptr, int* src, int* tgt, cudaStream_t st) {
     dim3 g(cap_cells, n_img);
     const size_t smem = (size_t)WARPS * ((n_atoms + 31) / 32) * sizeof(unsigned);
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
-        UMAB_CUDA(cudaFuncSetAttribute(neighbor_cell_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // the opt-in above 48 KB is a per-device attribute; engines on several GPUs run on their own host threads
+    static std::mutex mu;
+    static size_t configured[64] = {0};
+    if (smem > 227 * 1024) throw CudaError("neighbour search: image too large for the shared-memory bitmap (> ~226k atoms)");
+    if (smem > 40 * 1024) {
+        int dev = 0;
+        UMAB_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (smem > configured[dev & 63]) {
+            UMAB_CUDA(cudaFuncSetAttribute(neighbor_cell_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[dev & 63] = smem;
+        }
     }
     neighbor_cell_kernel<1><<<g, WARPS * 32, smem, st>>>(pos, n_atoms, cutoff * cutoff, cap, cap_cells,
                                                          reinterpret_cast<const CellGrid*>(grid), cell_start, cell_atoms,

@@ -81,20 +81,50 @@ except Exception:
     HAVE_ASE = False
     all_changes = ["positions", "numbers", "cell", "pbc", "initial_charges", "initial_magmoms"]
 
-    class _ASEBase:  # minimal stand-in of ase.calculators.calculator.Calculator
+    class _ASEBase:
+        """Stand-in of ``ase.calculators.calculator.Calculator`` with ASE's caching protocol: ``get_property``
+        compares the queried Atoms with the stored COPY (``check_state``), clears ``results`` on any change and
+        calls ``calculate`` only when the property is not cached; the base ``calculate`` stores ``atoms.copy()``."""
         implemented_properties: List[str] = []
 
         def __init__(self, **kwargs):
             self.results = {}
             self.atoms = None
 
+        def check_state(self, atoms, tol=1e-15):
+            if self.atoms is None:
+                return list(all_changes)
+            changes = []
+            a = np.asarray(self.atoms.get_positions(), dtype=np.float64)
+            b = np.asarray(atoms.get_positions(), dtype=np.float64)
+            if a.shape != b.shape or np.abs(a - b).max(initial=0.0) > tol:
+                changes.append("positions")
+            if list(self.atoms.get_chemical_symbols()) != list(atoms.get_chemical_symbols()):
+                changes.append("numbers")
+            return changes
+
+        def get_property(self, name, atoms=None, allow_calculation=True):
+            if atoms is None:
+                atoms, system_changes = self.atoms, []
+            else:
+                system_changes = self.check_state(atoms)
+                if system_changes:
+                    self.results = {}
+            if name not in self.results:
+                if not allow_calculation:
+                    return None
+                self.calculate(atoms, [name], system_changes)
+            return self.results[name]
+
+        def calculate(self, atoms=None, properties=("energy",), system_changes=tuple(all_changes)):
+            if atoms is not None:
+                self.atoms = atoms.copy()
+
         def get_potential_energy(self, atoms=None, force_consistent=False):
-            self.calculate(atoms or self.atoms, ["energy"], all_changes)
-            return self.results["energy"]
+            return self.get_property("energy", atoms)
 
         def get_forces(self, atoms=None):
-            self.calculate(atoms or self.atoms, ["forces"], all_changes)
-            return self.results["forces"]
+            return self.get_property("forces", atoms)
 
 
 class UMAASECalculator(_ASEBase):
@@ -112,7 +142,10 @@ class UMAASECalculator(_ASEBase):
     def calculate(self, atoms=None, properties=("energy",), system_changes=tuple(all_changes)):
         if atoms is None:
             atoms = self.atoms
-        self.atoms = atoms
+        # ASE's base class stores atoms.copy(): the cache check of the next query (check_state) must compare the
+        # new geometry with a SNAPSHOT, never with the caller's live object (reference: FAIRChemCalculator.calculate
+        # calls Calculator.calculate first)
+        super().calculate(atoms, properties, system_changes)
         if self._pool is not None:
             e, f = self._pool.result_for(self._slot)
         else:

@@ -43,3 +43,21 @@ def built_lib():
     """The in-tree CUDA library (built on demand; nvcc cross-compiles without a GPU)."""
     from pdb2reaction_b200.csrc import build as b
     return b.build()
+
+
+@pytest.fixture()
+def small_model(state4, arch4, monkeypatch):
+    """Route model='test-4x' to the 4-expert test weights (the default ID means 32 experts)."""
+    from pdb2reaction_b200 import calculator as calc_mod
+    from pdb2reaction_b200.checkpoint import EnergyTransform
+    monkeypatch.setattr(calc_mod, "load_model_state", lambda model, arch, task_name="omol": (state4, EnergyTransform()))
+    orig = calc_mod.CudaBackend.__init__
+
+    def init(self, elem, **kw):
+        kw["arch"] = arch4
+        orig(self, elem, **kw)
+
+    monkeypatch.setattr(calc_mod.CudaBackend, "__init__", init)
+    calc_mod._engine_cache.clear()
+    yield
+    calc_mod._engine_cache.clear()

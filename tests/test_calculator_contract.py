@@ -153,3 +153,32 @@ def test_fd_hessian_of_oracle_matches_its_analytic_hessian(state4, arch4, hyper4
     h_an = 0.5 * (h_an + h_an.T)
     # float32 forces (the backend interface returns fp32) differenced over 2e-3 A: ~1e-3 eV/A^2 noise
     assert np.abs(h_fd - h_an).max() < 5e-3
+
+
+def test_model_id_without_checkpoint_raises_and_random_weights_are_opt_in(monkeypatch, arch4):
+    """The reference fails hard when the checkpoint of a model ID cannot be obtained (uma_pysis.py:246-250); a drop-in
+    must not silently answer with random weights."""
+    from pdb2reaction_b200 import calculator as cm
+    monkeypatch.delenv("UMAB_WEIGHTS", raising=False)
+    monkeypatch.delenv("UMAB_ALLOW_RANDOM_WEIGHTS", raising=False)
+    monkeypatch.setattr(cm, "_state_cache", {})
+    with pytest.raises(FileNotFoundError, match="random:uma-s-1p1"):
+        cm.load_model_state("uma-s-1p1", arch4)
+    state, tr = cm.load_model_state("random:uma-s-1p1", arch4)
+    assert tr.is_identity and "sphere_embedding.weight" in state
+    monkeypatch.setenv("UMAB_ALLOW_RANDOM_WEIGHTS", "1")
+    state2, _ = cm.load_model_state("uma-s-1p1", arch4)
+    assert torch.equal(state2["sphere_embedding.weight"], state["sphere_embedding.weight"])
+
+
+def test_engine_cache_is_bounded_lru(monkeypatch):
+    from pdb2reaction_b200 import calculator as cm
+    monkeypatch.setattr(cm, "_engine_cache", cm.OrderedDict())
+    monkeypatch.setattr(cm, "ENGINE_CACHE_MAX", 2)
+    for i in range(4):
+        cm._engine_cache_put(("w", i, 0), f"eng{i}")
+    cm._engine_cache_put(("w", 9, 1), "other-device")                  # the bound is per device
+    assert list(cm._engine_cache) == [("w", 2, 0), ("w", 3, 0), ("w", 9, 1)]
+    assert cm._engine_cache_get(("w", 2, 0)) == "eng2"                 # a hit refreshes the entry
+    cm._engine_cache_put(("w", 5, 0), "eng5")
+    assert list(cm._engine_cache) == [("w", 9, 1), ("w", 2, 0), ("w", 5, 0)]

@@ -32,6 +32,9 @@ class Atoms:                      # ase.Atoms-like
     def __init__(self, sym, pos):
         self.sym, self.pos, self.calc = list(sym), np.array(pos, dtype=np.float64), None
 
+    def copy(self):
+        return Atoms(self.sym, self.pos.copy())
+
     def get_chemical_symbols(self):
         return self.sym
 
@@ -84,6 +87,34 @@ def test_ase_shim_units_and_shared_batch():
     assert be.calls[-1] == (6, True) and len(be.calls) == 2
     ref_e, ref_f = be.evaluate(np.stack(_imgs(6)))
     assert np.allclose(es, ref_e, atol=1e-9) and np.allclose(np.stack(fs), ref_f, atol=1e-6)
+
+
+def test_ase_shim_never_serves_stale_results_after_an_in_place_move():
+    """ASE caches results against a COPY of the Atoms (check_state).  A calculator that aliased the caller's live
+    object would compare it with itself and return the first geometry's results forever."""
+    be = SpringBackend()
+    calc = uma_pysis(_backend=be)
+    at = Atoms(ELEM, X)
+    at.calc = UMAASECalculator(calc)
+    e0, f0 = at.get_potential_energy(), at.get_forces().copy()
+    n0 = len(be.calls)
+    assert at.get_potential_energy() == e0 and len(be.calls) == n0         # unchanged geometry: served from the cache
+    assert at.calc.atoms is not at
+    at.pos[1, 0] += 0.2                                                     # in-place move of the SAME object
+    e1, f1 = at.get_potential_energy(), at.get_forces()
+    assert len(be.calls) == n0 + 1 and e1 != e0 and np.abs(f1 - f0).max() > 1e-3
+    ref_e, ref_f = be.evaluate(at.pos[None])
+    assert abs(e1 - ref_e[0]) < 1e-9 and np.allclose(f1, ref_f[0], atol=1e-6)
+    # shared batch: images moved in place are re-evaluated together, once
+    images = [Atoms(ELEM, x) for x in _imgs(4)]
+    SharedImageBatch(images, calc)
+    [im.get_forces() for im in images]
+    be.calls.clear()
+    for im in images:
+        im.pos += 0.01
+    fs = np.stack([im.get_forces() for im in images])
+    assert be.calls == [(4, True)]
+    assert np.allclose(fs, be.evaluate(np.stack([im.pos for im in images]))[1], atol=1e-6)
 
 
 def test_recompute_energies_is_one_call():

@@ -11,23 +11,6 @@ from conftest import merged_for
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture()
-def small_model(state4, arch4, monkeypatch):
-    """Route model='test-4x' to the 4-expert test weights (the default ID means 32 experts)."""
-    from pdb2reaction_b200.checkpoint import EnergyTransform
-    monkeypatch.setattr(calc_mod, "load_model_state", lambda model, arch, task_name="omol": (state4, EnergyTransform()))
-    orig = calc_mod.CudaBackend.__init__
-
-    def init(self, elem, **kw):
-        kw["arch"] = arch4
-        orig(self, elem, **kw)
-
-    monkeypatch.setattr(calc_mod.CudaBackend, "__init__", init)
-    calc_mod._engine_cache.clear()
-    yield
-    calc_mod._engine_cache.clear()
-
-
 def test_get_forces_matches_oracle_in_atomic_units(built_lib, small_model, state4, arch4, hyper4):
     from oracle import uma_ref
     elem, imgs = synth.make_string(30, 3, 13)

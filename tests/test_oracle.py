@@ -156,3 +156,16 @@ def test_hessian_is_symmetric_and_matches_fd_of_forces(state4, arch4, hyper4):
     g2, = torch.autograd.grad(uma_ref.energy(merged, p2, zz, nat, ei, hp=hyper4).sum(), p2)
     col = (g1 - g2).reshape(-1) / (2 * step)
     assert (col - h[:, k]).abs().max() < 1e-5
+
+
+def test_fp32_oracle_agrees_with_the_committed_float64_fixture(arch4, state4, hyper4):
+    """tests/golden/large/hess_n160.npz (float64 oracle): the float32 oracle -- what the CUDA path is compared with in
+    the seeded-cluster tests -- sits well inside the north-star tolerances of it."""
+    import os
+    from conftest import merged_for
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "large", "hess_n160.npz"))
+    elem, coords = synth.make_cluster(int(g["n_atoms"]), int(g["seed"]))
+    z, merged = merged_for(state4, arch4, elem)
+    e, f = uma_ref.OracleUMA(merged, z, dtype=torch.float32, hyper=hyper4).energy_forces(coords)
+    assert abs(e.item() - g["energy"][0]) / 160 < 1e-5
+    assert np.abs(f[0].double().numpy() - g["forces"]).max() < 1e-4

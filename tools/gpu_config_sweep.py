@@ -10,7 +10,7 @@ names = sys.argv[1:] or ["C1", "C2", "C3", "C4", "C5"]
 for name in names:
     elem, imgs = synth.make_config(name)
     b, n = imgs.shape[0], imgs.shape[1]
-    calc = uma_pysis()
+    calc = uma_pysis(model="random:uma-s-1p1")
     c = imgs.reshape(b, -1) * ANG2BOHR
     calc.get_forces_batch(elem, c)                          # engine build + warm-up
     torch.cuda.synchronize()

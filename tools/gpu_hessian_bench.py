@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 workers = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 mode = sys.argv[3] if len(sys.argv) > 3 else "FiniteDifference"
 elem, coords = synth.make_cluster(n, 3)
-calc = uma_pysis(workers=workers, hessian_calc_mode=mode)
+calc = uma_pysis(model="random:uma-s-1p1", workers=workers, hessian_calc_mode=mode)
 calc.get_forces(elem, coords * ANG2BOHR)                 # engine build + warm-up
 torch.cuda.synchronize()
 t0 = time.perf_counter()

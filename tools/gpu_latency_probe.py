@@ -8,7 +8,7 @@ warnings.simplefilter("ignore")
 elem, imgs = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C2")
 b = imgs.shape[0]
 c = imgs.reshape(b, -1) * ANG2BOHR
-calc = uma_pysis()
+calc = uma_pysis(model="random:uma-s-1p1")
 def lat(tag, k=8):
     ts = []
     for i in range(k):

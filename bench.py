@@ -8,6 +8,12 @@ One "step" = one pass of the hot path over the batch: every image of the string 
 rebuilt (as the reference does on each call), its energy and its forces.  Workload = BASELINE.json
 configs[3]: a 32-image string on a 1500-atom cluster model (synthetic, deterministic), random-init
 uma-s-1p1-architecture weights.  Prints ONE JSON line (see the keys below / DESIGN.md).
+
+N > 1 (torchrun, one rank per GPU): STRONG scaling of that one string -- rank r evaluates images
+shard_bounds(32, N)[r], one NCCL all_gather of the packed [E | F] records per step; `value` = 32 images /
+max-over-ranks device time.  `e2e` goes through the product call sharding.sharded_get_forces_batch: host
+coordinates on rank 0 -> broadcast -> shard evaluation -> all_gather -> the full host result on every rank.
+A short weak-scaled pass (every rank a whole string) is reported under the `weak` key.
 """
 from __future__ import annotations
 
@@ -39,7 +45,9 @@ def parse():
     p.add_argument("--atoms", type=int, default=1500)
     p.add_argument("--images", type=int, default=32)
     p.add_argument("--seed", type=int, default=4)
-    p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    p.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                   help="strong (default): the ONE 32-image string of BASELINE.json configs[3] is sharded 32/N images per "
+                        "GPU; weak: every GPU gets a 32-image string of its own (reported as the `weak` key otherwise)")
     p.add_argument("--gemm", default=os.environ.get("UMAB_GEMM", "auto"), choices=["auto", "simt", "tc"])   # auto = engine default
     p.add_argument("--experts", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -179,7 +187,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     elem, imgs = synth.make_string(args.atoms, args.images, args.seed)
-    n_s, elem_s, imgs_s, orc, _ = choose_cpu_sample(args, elem, imgs, args.steps + args.warmup, budget_s=200.0)
+    # on-config: whole images whenever their (steps + warmup) evaluations fit ~7 minutes (C4: 25 x ~12 s = 5 min)
+    n_s, elem_s, imgs_s, orc, _ = choose_cpu_sample(args, elem, imgs, args.steps + args.warmup, budget_s=420.0)
     for w in range(args.warmup):
         orc.energy_forces(imgs_s[w % len(imgs_s)])
     t0 = time.perf_counter()
@@ -188,9 +197,11 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     atoms_per_s = args.steps * n_s / dt
     val = atoms_per_s / args.atoms
-    what = "one whole image" if n_s == args.atoms else f"a {n_s}-atom sub-cluster of one {args.atoms}-atom image"
-    sample = (f"per step: energy+forces of {what} (graph rebuilt, fp32, batch of 1, edge-chunked autograd; the largest "
-              f"sample whose {args.steps}+{args.warmup} evaluations fit ~200 s); value = atoms/s / {args.atoms}")
+    same = n_s == args.atoms
+    what = "one whole image" if same else f"a {n_s}-atom sub-cluster of one {args.atoms}-atom image"
+    sample = (f"per step: energy+forces of {what} of the string (graph rebuilt, fp32, batch of 1, edge-chunked autograd: "
+              f"the reference's one-image-per-call pattern); {args.steps}+{args.warmup} evaluations; "
+              + ("value = image evaluations / s" if same else f"value = atoms/s / {args.atoms} (extrapolated by atoms)"))
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
@@ -199,6 +210,7 @@ def run_reference(args):
         "config": {"workload": f"C4: DMF/GSM string, {args.images} images x {args.atoms} atoms (BASELINE.json configs[3])",
                    "n_atoms": args.atoms, "n_images": args.images, "weights": "random-init uma-s-1p1 architecture, seed 0"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "same_config": bool(same),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -300,7 +312,7 @@ def main():
 
     from pdb2reaction_b200 import calculator as calc_mod
     from pdb2reaction_b200 import engine as engine_mod
-    from pdb2reaction_b200 import uma_pysis
+    from pdb2reaction_b200 import synth, uma_pysis
     from pdb2reaction_b200.arch import UMAArch
     from pdb2reaction_b200.shims import ANG2BOHR
 
@@ -308,6 +320,7 @@ def main():
     gemm_name = args.gemm if args.gemm != "auto" else ("tc" if args.atoms >= 100 else "simt")
     elem, imgs, total_images = build_inputs(args, rank, world)
     n_local = imgs.shape[0]
+    shard_cap = -(-args.images // world) if args.scaling == "strong" else n_local      # fixed record size on every rank
     arch = UMAArch(num_experts=args.experts)
     if args.experts != 32:
         orig = calc_mod.CudaBackend.__init__
@@ -324,7 +337,7 @@ def main():
         e, f = eng.energy_forces(pos_dev)
         if world > 1:                                   # the one collective of the path
             from pdb2reaction_b200.sharding import pack_results
-            rec = pack_results(e, f, n_local, args.atoms)
+            rec = pack_results(e, f, shard_cap, args.atoms)
             out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
             dist.all_gather_into_tensor(out, rec)
         return e, f
@@ -368,19 +381,36 @@ def main():
     fam = eng.profile_read()
     eng.profile(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    et = torch.tensor([float(n_edges)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(et, op=dist.ReduceOp.SUM)
     ms_tot = t.item()
+    edges_tot = et.item()
     value = total_images * args.steps / (ms_tot / 1e3)
 
     # ---------------- end to end through the public calculator API (`e2e`)
-    coords_bohr = (imgs * ANG2BOHR).reshape(n_local, -1)
+    # host coordinates of the WHOLE string on the optimizer's rank -> (N > 1: broadcast, shard, all_gather) -> the whole
+    # string's energies / forces as host numpy on every rank, in Hartree / Hartree per Bohr
+    from pdb2reaction_b200.sharding import sharded_get_forces_batch
+    if args.scaling == "strong":
+        imgs_all = synth.make_string(args.atoms, args.images, args.seed)[1]
+    else:
+        imgs_all = imgs
+    coords_all = (imgs_all * ANG2BOHR).reshape(imgs_all.shape[0], -1)
+    coords_arg = coords_all if (rank == 0 or args.scaling == "weak") else np.zeros_like(coords_all)
+
+    def e2e_call():
+        if args.scaling == "strong":
+            return sharded_get_forces_batch(calc, elem, coords_arg)
+        return calc.get_forces_batch(elem, coords_arg)
+
     for _ in range(min(2, args.warmup)):
-        calc.get_forces_batch(elem, coords_bohr)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = calc.get_forces_batch(elem, coords_bohr)
+        res = e2e_call()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -388,6 +418,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = total_images * args.steps / t.item()
     assert np.isfinite(res["energy"]).all() and np.isfinite(res["forces"]).all()
+    assert res["forces"].shape == (coords_all.shape[0], 3 * args.atoms)
+
+    # ---------------- weak-scaled companion (N > 1 only): every rank a whole string of its own, no gather needed
+    weak = None
+    if world > 1 and args.scaling == "strong":
+        imgs_w = synth.make_string(args.atoms, args.images, args.seed)[1]
+        pos_w = torch.from_numpy((imgs_w + np.random.default_rng(1000 + rank).normal(scale=0.02, size=imgs_w.shape)).astype(np.float32)).cuda()
+        wsteps = max(2, min(args.steps, 4))
+        eng.energy_forces(pos_w)
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0.record()
+        for _ in range(wsteps):
+            e_w, f_w = eng.energy_forces(pos_w)
+            from pdb2reaction_b200.sharding import pack_results
+            rec = pack_results(e_w, f_w, args.images, args.atoms)
+            outw = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
+            dist.all_gather_into_tensor(outw, rec)
+        w1.record()
+        barrier()
+        tw = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak = {"value": world * args.images * wsteps / (tw.item() / 1e3), "unit": UNIT, "steps": wsteps,
+                "images_in_job": world * args.images, "n_images_per_gpu": args.images,
+                "note": "weak scaling (per-GPU work fixed at a whole 32-image string); not the headline"}
 
     if rank == 0:
         pk = peaks()
@@ -434,34 +489,51 @@ def main():
             "dtype": "f32" if gemm_name == "simt" else "f32 (bf16x3 split tensor-core GEMMs, fp32 accumulate)",
             "data": "synthetic",
             "atoms_per_s": value * args.atoms,
-            "config": {"workload": f"C4: DMF/GSM string, {args.images} images x {args.atoms} atoms per GPU-batch "
-                                   f"(BASELINE.json configs[3]); {total_images} images in the job",
-                       "n_atoms": args.atoms, "n_images_per_gpu": n_local, "edges_per_gpu_step": int(edges_per_step),
+            "config": {"workload": (f"C4: ONE DMF/GSM string of {args.images} images x {args.atoms} atoms (BASELINE.json "
+                                    f"configs[3]), images sharded {args.images}/{world} per GPU; {total_images} images in the job"
+                                    if args.scaling == "strong" else
+                                    f"C4-shaped strings, {args.images} images x {args.atoms} atoms PER GPU (weak scaling); "
+                                    f"{total_images} images in the job"),
+                       "n_atoms": args.atoms, "n_images": total_images, "n_images_per_gpu": n_local,
+                       "edges_per_gpu_step": int(edges_per_step),
                        "weights": f"random-init uma-s-1p1 architecture ({args.experts} experts merged), seed 0",
                        "gemm": gemm_name, "l2": "working set (GBs of per-edge activations) >> 126 MB L2; no flush needed",
                        "collective": "all_gather of [E|F] per step" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(n_local * args.atoms * 12),
-                    "d2h_bytes_per_step": int(n_local * (8 + args.atoms * 12)),
-                    "api": "uma_pysis.get_forces_batch(elem, coords_bohr) -> host numpy (Hartree, Hartree/Bohr)"},
+                    "d2h_bytes_per_step": int((total_images if args.scaling == "strong" else n_local) * (8 + args.atoms * 12)),
+                    "api": ("uma_pysis.get_forces_batch(elem, coords_bohr) -> host numpy (Hartree, Hartree/Bohr)" if world == 1 else
+                            "sharding.sharded_get_forces_batch(calc, elem, coords_bohr): rank-0 host coordinates -> NCCL broadcast "
+                            "-> shard evaluation -> one all_gather -> the WHOLE string's host numpy result on every rank")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
             "kernel_families": fam_out,
             "profiled_pass_ms_per_step": prof_ms_per_step,
-            "model_tflops_algorithmic": edges_per_step * FLOP_PER_EDGE_EF * world / (ms_tot / args.steps * 1e-3) / 1e12,
+            "model_tflops_algorithmic": edges_tot * FLOP_PER_EDGE_EF / (ms_tot / args.steps * 1e-3) / 1e12,
         }
+        if weak is not None:
+            out["weak"] = weak
         if world == 1 and not args.no_cpu_baseline:
             n_s, elem_s, imgs_s, orc, t_probe = choose_cpu_sample(args, elem, imgs, 1, budget_s=45.0)
             t0 = time.perf_counter()
             reps = 1 if n_s == args.atoms else 2
             for k in range(reps):
-                orc.energy_forces(imgs_s[k % len(imgs_s)])
+                e_cpu, f_cpu = orc.energy_forces(imgs_s[k % len(imgs_s)])
             dtc = (time.perf_counter() - t0) / reps
             what = "one whole image" if n_s == args.atoms else f"a {n_s}-atom sub-cluster of one image"
             out["cpu_baseline"] = {"value": n_s / dtc / args.atoms, "unit": UNIT, "cores": torch.get_num_threads(),
                                    "kind": "port",
                                    "sample": f"energy+forces of {what}, oracle fp32, graph rebuilt, {dtc:.1f} s per "
                                              f"evaluation ({t_probe:.1f} s for the 300-atom probe); value = atoms/s / {args.atoms}"}
+            if n_s == args.atoms:
+                # the whole image the CPU leg just evaluated is image 0 of the timed batch: the bench checks its own
+                # GPU numbers against the oracle (north-star tolerances) and refuses to report a wrong-but-fast result
+                de = abs(float(e_last[0]) - float(e_cpu[0])) / args.atoms
+                df = float(np.abs(f_last[0].cpu().numpy() - f_cpu[0].numpy()).max())
+                out["parity"] = {"checked": "image 0 of the timed batch vs the fp32 oracle on the host cores",
+                                 "dE_eV_per_atom": de, "tol_dE": 1e-5, "dF_eV_per_A": df, "tol_dF": 1e-4,
+                                 "ok": bool(de < 1e-5 and df < 1e-4)}
+                assert out["parity"]["ok"], f"bench parity check failed: {out['parity']}"
         emit(out)
     if world > 1:
         dist.destroy_process_group()

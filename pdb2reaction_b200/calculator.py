@@ -195,6 +195,19 @@ class CudaBackend:
                 f_out *= np.float32(self.transform.scale)
         return e_out, f_out
 
+    def evaluate_device(self, coords_ang: np.ndarray):
+        """coords [B,N,3] A -> (E [B] fp64 eV, F [B,N,3] fp32 eV/A) as tensors on the FIRST engine's GPU (one pinned
+        H2D of the coordinates, no D2H): the shard evaluation of ``sharding.sharded_get_forces_batch``."""
+        eng = self.engines[0]
+        dev = torch.device("cuda", eng.device)
+        pos = torch.from_numpy(np.ascontiguousarray(coords_ang, dtype=np.float32))
+        with torch.cuda.device(dev):
+            e, f = eng.energy_forces(pos.pin_memory().to(dev, non_blocking=True), True)
+        if not self.transform.is_identity:
+            e = e * self.transform.scale + torch.as_tensor(self._e_const, device=dev)
+            f = f * float(self.transform.scale)
+        return e, f
+
     def forces_device(self, coords_ang: np.ndarray) -> torch.Tensor:
         """coords [B,N,3] A -> forces [B,N,3] fp32 eV/A as ONE tensor on the first GPU: shards are evaluated on
         their GPUs and gathered device-to-device (no host copy of the results) -- feeds the on-device FD Hessian."""

@@ -115,6 +115,11 @@ struct GemmArgs {
     int batch = 1;
     int wsel[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // weight index per batch entry
     int accumulate = 0;
+    // precision study only (tools/gpu_precision_study.py): operand rounding emulated in the fp32 SIMT kernel.
+    // 0 exact fp32; 1 single-pass TF32 (both operands rounded to 10 mantissa bits); 2 bf16 x2 with the weights
+    // rounded to bf16 (a_hi w_hi + a_lo w_hi); 3 bf16 x2 with the activations rounded to bf16 (a_hi w_hi + a_hi w_lo);
+    // 4 single-pass bf16
+    int round_mode = 0;
 };
 
 void gemm_simt(const GemmArgs& a, cudaStream_t st);

@@ -312,7 +312,12 @@ struct umab_engine {
     // choice depends on the image size only, never on the batch, so an image evaluated alone and
     // inside a batch goes through the same arithmetic.
     bool use_tc() const { return cfg.gemm_mode == 1 || (cfg.gemm_mode == 2 && n_atoms >= 100); }
-    void gemm(const GemmArgs& a, cudaStream_t st) {
+    // precision study (set by umab_set_option "simt_round_fwd" / "simt_round_bwd"; SIMT path only)
+    int simt_round_fwd = 0, simt_round_bwd = 0;
+    bool in_backward = false;
+    void gemm(const GemmArgs& a_in, cudaStream_t st) {
+        GemmArgs a = a_in;
+        a.round_mode = in_backward ? simt_round_bwd : simt_round_fwd;
         timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
             if (a.A_hi) gemm_tc2(a, st, tc2_cache, 0);
             else if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
@@ -698,6 +703,8 @@ struct umab_engine {
         if (!want_f) return;
 
         // ================= backward: dE_total/dpos
+        in_backward = true;
+        struct Leave { bool& f; ~Leave() { f = false; } } leave{in_backward};
         gx.ensure<S>(nf); gx1.ensure<S>(nf); gn.ensure<S>(nf); ggp.ensure<S>((size_t)n_nodes * 2 * H * 4);
         gs1.ensure<S>((size_t)n_nodes * H * 4);
         if (!chunks_closed) Gbuf.ensure<S>(ne * 9 * C * 4);
@@ -856,6 +863,10 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
     if (n == "neighbor_mode") {
         if (value < 0 || value > 2) throw CudaError("neighbor_mode: 0 auto, 1 brute force, 2 cell list");
         e->neighbor_mode = (int)value;
+    } else if (n == "simt_round_fwd" || n == "simt_round_bwd") {
+        // precision study: operand rounding emulated by the fp32 SIMT GEMM (GemmArgs::round_mode), forward / adjoint GEMMs
+        if (value < 0 || value > 4) throw CudaError("simt_round_*: 0 exact, 1 tf32, 2 bf16x2 (W bf16), 3 bf16x2 (A bf16), 4 bf16");
+        (n == "simt_round_fwd" ? e->simt_round_fwd : e->simt_round_bwd) = (int)value;
     } else {
         throw CudaError("unknown option: " + n);
     }

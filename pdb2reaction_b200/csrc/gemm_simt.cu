@@ -12,6 +12,21 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, NT = 256;
 
+// operand rounding of the precision study (GemmArgs::round_mode); never active on the product path
+__device__ __forceinline__ float rnd_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float rnd_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float rnd_bf16x2(float x) { const float h = rnd_bf16(x); return h + rnd_bf16(x - h); }
+__device__ __forceinline__ float rnd_a(float x, int mode) {
+    return mode == 1 ? rnd_tf32(x) : mode == 2 ? rnd_bf16x2(x) : (mode == 3 || mode == 4) ? rnd_bf16(x) : x;
+}
+__device__ __forceinline__ float rnd_w(float x, int mode) {
+    return mode == 1 ? rnd_tf32(x) : mode == 3 ? rnd_bf16x2(x) : (mode == 2 || mode == 4) ? rnd_bf16(x) : x;
+}
+
 __global__ void __launch_bounds__(NT, 2)
 gemm_simt_kernel(GemmArgs g) {
     __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -39,6 +54,14 @@ gemm_simt_kernel(GemmArgs g) {
             ra[i] = (r < M) ? ld4(A + r * g.lda + k0 + lk) : f4zero();
             int n = n0 + lrow0 + i * 64;
             rb[i] = (n < N) ? ld4(W + (long long)n * g.ldw + k0 + lk) : f4zero();
+        }
+        if (g.round_mode) {
+            const int rm = g.round_mode;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                ra[i] = make_float4(rnd_a(ra[i].x, rm), rnd_a(ra[i].y, rm), rnd_a(ra[i].z, rm), rnd_a(ra[i].w, rm));
+                rb[i] = make_float4(rnd_w(rb[i].x, rm), rnd_w(rb[i].y, rm), rnd_w(rb[i].z, rm), rnd_w(rb[i].w, rm));
+            }
         }
     };
     auto store_tiles = [&](int buf) {

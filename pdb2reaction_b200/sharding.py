@@ -49,7 +49,7 @@ def pack_results(e: torch.Tensor, f: torch.Tensor, cap: int, n_atoms: int) -> to
 
 
 def unpack_results(rec: torch.Tensor, b: int, cap: int, n_atoms: int):
-    e = rec[: 2 * b].contiguous().view(torch.float64)
+    e = rec[: 2 * b].clone().view(torch.float64)          # clone: a row of an all_gather buffer may sit at an odd fp32 offset
     f = rec[2 * cap: 2 * cap + b * n_atoms * 3].reshape(b, n_atoms, 3)
     return e, f
 
@@ -87,6 +87,53 @@ class SpmdEvaluator:
             fs.append(fr)
         return torch.cat(es), torch.cat(fs)
 
+
+
+def sharded_get_forces_batch(calc, elem, coords_bohr, group: Optional[dist.ProcessGroup] = None, src: int = 0):
+    """``calc.get_forces_batch(elem, coords_bohr)`` with the IMAGES of the string sharded over the ranks of ``group``
+    (one process per GPU under torchrun; the new meaning of ``workers``, reference ``uma_pysis.py:205-242``).
+
+    The optimizer lives on rank ``src``: its host coordinates [B, 3N] (Bohr) are broadcast, rank r evaluates the
+    contiguous block ``shard_bounds(B, world)[r]`` on its own device with its replica of the weights, ONE all_gather
+    of the packed ``[E | F]`` records follows, and every rank returns the full host result
+    ``{"energy": [B] Hartree, "forces": [B, 3N] Hartree/Bohr}`` -- identical bits to the single-process call."""
+    from .calculator import EV2AU, F_EVAA_2_AU
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    calc._ensure_core(elem)
+    if world == 1:
+        return calc.get_forces_batch(elem, coords_bohr)
+    core = calc._core
+    n_atoms = len(core.elem)
+    dev = core.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    c = torch.as_tensor(np.ascontiguousarray(np.asarray(coords_bohr, dtype=np.float64).reshape(-1, 3 * n_atoms)))
+    c = c.to(dev)
+    dist.broadcast(c, src=src, group=group)                  # coordinates of the step: B x 3N fp64 (C4: 1.15 MB)
+    b_tot = c.shape[0]
+    bounds = shard_bounds(b_tot, world)
+    lo, hi = bounds[rank]
+    cap = max(h - l for l, h in bounds)
+    backend = core.backend
+    if hi > lo and dev.type == "cuda" and hasattr(backend, "evaluate_device"):
+        e, f = backend.evaluate_device(calc._coords_ang(c[lo:hi].cpu().numpy(), batch=True))     # results stay on the GPU
+    elif hi > lo:
+        r = core.compute_batch(calc._coords_ang(c[lo:hi].cpu().numpy(), batch=True), forces=True)
+        e, f = torch.from_numpy(r["energy"]).to(dev), torch.from_numpy(r["forces"]).to(dev)
+    else:
+        e = torch.zeros(0, dtype=torch.float64, device=dev)
+        f = torch.zeros((0, n_atoms, 3), dtype=torch.float32, device=dev)
+    rec = pack_results(e, f, cap, n_atoms)
+    out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=dev)
+    dist.all_gather_into_tensor(out, rec, group=group)       # the ONE collective of the step
+    out = out.cpu().view(world, -1)
+    es, fs = [], []
+    for r_, (l, h) in enumerate(bounds):
+        er, fr = unpack_results(out[r_], h - l, cap, n_atoms)
+        es.append(er)
+        fs.append(fr)
+    e_all = torch.cat(es).numpy()
+    f_all = calc._zero_frozen_forces_ev(torch.cat(fs).numpy())
+    return {"energy": e_all * EV2AU, "forces": (np.asarray(f_all, dtype=np.float64) * F_EVAA_2_AU).reshape(b_tot, -1)}
 
 
 def sharded_fd_hessian(calc, elem, coords_bohr, group: Optional[dist.ProcessGroup] = None):

@@ -111,3 +111,49 @@ def test_sharded_fd_hessian_gloo_world2(frozen, partial, shape):
         assert p.exitcode == 0
     for rank, ok, shp in res:
         assert ok and shp == shape
+
+
+def _string_worker(rank, world, port, n_img, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from helpers import SpringBackend
+    from pdb2reaction_b200 import uma_pysis
+    from pdb2reaction_b200.sharding import sharded_get_forces_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        elem = ["C", "H", "H", "O", "N"]
+        rng = np.random.default_rng(3)
+        x = np.array([[0, 0, 0], [1.1, 0, 0], [0, 1.0, 0.2], [0.3, -0.9, 0.8], [-1.0, 0.2, 0.5]]) / 0.529177210903
+        coords = np.stack([x + 0.05 * rng.normal(size=x.shape) for _ in range(n_img)]).reshape(n_img, -1)
+        mine = coords if rank == 0 else np.zeros_like(coords)          # only the optimizer's rank holds the geometry
+        full = uma_pysis(_backend=SpringBackend(), freeze_atoms=[2]).get_forces_batch(elem, coords)
+        be = SpringBackend()
+        shard = sharded_get_forces_batch(uma_pysis(_backend=be, freeze_atoms=[2]), elem, mine)
+        ok = np.array_equal(full["energy"], shard["energy"]) and np.array_equal(full["forces"], shard["forces"])
+        q.put((rank, bool(ok), sum(b for b, _ in be.calls), tuple(shard["forces"].shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_img", [6, 5, 1])
+def test_sharded_get_forces_batch_gloo_world2(n_img):
+    """The strong-scaled string step (bench.py --gpus N): coordinates broadcast from the optimizer's rank, images
+    sharded, one all_gather -> every rank holds the single-process result, bit for bit; each rank evaluated only its
+    block."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_string_worker, args=(r, 2, port, n_img, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bounds = shard_bounds(n_img, 2)
+    for rank, ok, n_eval, shp in res:
+        assert ok and shp == (n_img, 15)
+        assert n_eval == bounds[rank][1] - bounds[rank][0]

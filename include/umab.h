@@ -59,7 +59,9 @@ typedef struct umab_config {
 } umab_config;
 
 /* ABI version of this header; umab_abi_version() must return the same value. */
-#define UMAB_ABI_VERSION 6
+#define UMAB_ABI_VERSION 7
+/* return code of umab_last_call: the sync-free graph build of the last call overflowed its edge capacity */
+#define UMAB_RETRY 2
 
 UMAB_API int32_t umab_abi_version(void);
 UMAB_API const char* umab_last_error(void);
@@ -73,8 +75,14 @@ UMAB_API int32_t umab_set_weight(umab_engine* e, const char* name, const float* 
 UMAB_API int32_t umab_finalize_weights(umab_engine* e);
 
 /* Run-time options.  "neighbor_mode": 0 = auto (shared-memory cell list from 128 atoms per image, brute
- * force below), 1 = brute force, 2 = cell list; both searches return the identical edge list. */
+ * force below), 1 = brute force, 2 = cell list; both searches return the identical edge list.
+ * "nosync" (default 1): sync-free graph build for calls that fit one chunk of the edge workspace;
+ * "cuda_graphs" (default 1): capture / replay of launch-bound umab_energy_forces_host calls;
+ * "simt_round_fwd" / "simt_round_bwd": operand rounding of the precision study (fp32 SIMT GEMMs only). */
 UMAB_API int32_t umab_set_option(umab_engine* e, const char* name, int64_t value);
+/* Read an option back, or a counter: "graph_replays", "graph_captures", "overflow_retries",
+ * "edges_per_image_seen". */
+UMAB_API int32_t umab_get_option(umab_engine* e, const char* name, int64_t* value);
 
 /* Atomic numbers of ONE image (host, n_atoms ints); all images share them. */
 UMAB_API int32_t umab_set_system(umab_engine* e, const int32_t* z_host, int32_t n_atoms);
@@ -87,11 +95,23 @@ UMAB_API int32_t umab_graph_copy(umab_engine* e, int32_t* src_dev, int32_t* tgt_
 
 /* Energies [n_images] (double, eV) and forces [n_images, n_atoms, 3] (fp32, eV/A; NULL = energy
  * only, skips the backward pass).  Device pointers.  Rebuilds the graph on every call, as the
- * reference does.  Synchronises `stream` once internally (edge-count read-back). */
+ * reference does.  Batches larger than the per-layer stores allow run as consecutive sub-batches inside
+ * the call.  Calls that fit ONE chunk of the edge workspace (a GSM string of 300-atom images, a 500-atom
+ * Hessian displacement batch, small molecules) do NOT synchronise the stream: the edge arrays are sized
+ * from a capacity (complete graph below 128 atoms per image, else the largest edges-per-image seen + 3 %)
+ * and an overflow is flagged on the device -- collect it with umab_last_call() after the stream has been
+ * synchronised and repeat the call on UMAB_RETRY.  Larger calls read the edge count back once. */
 UMAB_API int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_t n_images,
                            double* energy_dev, float* forces_dev, void* stream);
 
-/* Same with HOST buffers (pinned or pageable): H2D, compute, D2H and a final sync inside. */
+/* Images, edges (summed over the sub-batches) and sub-batches of the last umab_energy_forces* /
+ * umab_forces_jvp call.  Waits for the call's status words; returns UMAB_RETRY when its sync-free graph
+ * build overflowed (results invalid: repeat the call), 0 otherwise. */
+UMAB_API int32_t umab_last_call(umab_engine* e, int64_t* n_images, int64_t* n_edges, int64_t* n_subcalls);
+
+/* Same with HOST buffers (pinned or pageable): H2D, compute, D2H and a final sync inside (overflows of the
+ * sync-free path are handled inside).  Launch-bound calls are captured into a CUDA graph on their second
+ * occurrence and replayed as one graph launch afterwards (UMAB_CUDA_GRAPHS=0 disables). */
 UMAB_API int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n_images,
                                 double* energy_host, float* forces_host, void* stream);
 

@@ -23,6 +23,9 @@
 namespace umab {
 
 std::atomic<long long> g_launch_count{0};
+// bumped whenever any device / pinned buffer of the library is (re)allocated or freed: a captured CUDA graph bakes the
+// buffer addresses in, so it is replayed only while the generation it was captured under is still current
+std::atomic<long long> g_alloc_gen{0};
 struct TcPlaneCache;                                  // gemm_tc.cu
 TcPlaneCache* tc_cache_create();
 void tc_cache_destroy(TcPlaneCache* c);
@@ -53,6 +56,7 @@ struct DevBuf {
         if (bytes <= cap) return;
         if (p) { cudaFree(p); total -= (long long)cap; }
         p = nullptr; cap = 0;
+        ++g_alloc_gen;
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
@@ -69,7 +73,7 @@ struct DevBuf {
         cap = want;
         total += (long long)want;
     }
-    void release() { if (p) { cudaFree(p); total -= (long long)cap; } p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); total -= (long long)cap; ++g_alloc_gen; } p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
     float* f() const { return reinterpret_cast<float*>(p); }
     int* i() const { return reinterpret_cast<int*>(p); }
@@ -202,6 +206,32 @@ struct umab_engine {
     DevBuf cgrid, ccount, cstart, catoms, acell;       // cell list of the neighbour search
     int neighbor_mode = 0;                             // 0 auto (cell list from 128 atoms per image), 1 brute force, 2 cell list
     int* h_pinned = nullptr; size_t h_pinned_cap = 0;
+    // ---- sync-free graph build (single-chunk calls): the edge arrays are sized from a CAPACITY -- the complete graph
+    // for images below 128 atoms (cannot overflow), else the largest edges-per-image seen so far + 3 % -- instead of
+    // the row_ptr read-back; every per-edge kernel runs over the capacity (padding rows hold valid indices and are
+    // never reduced: all reductions walk the CSR), the by-source CSR takes the actual count from the device, and an
+    // overflow is flagged on the device, checked when the results are collected, and the call repeated.
+    long long hist_edges_per_image = 0;
+    bool fast_graph = false;                           // this evaluation ran on capacity-sized edge arrays
+    long long n_edges_actual = 0;                      // true edge count of the last evaluation (after resolve_status)
+    DevBuf status_dev;
+    int* h_status = nullptr;                           // pinned {actual edges, overflow}
+    cudaEvent_t status_ev = nullptr;
+    bool status_pending = false;
+    int status_nimg = 0;
+    long long total_mem = 0;                           // device memory size (store budget), queried once
+    // last public call (possibly several sub-batches)
+    long long call_images = 0, call_edges = 0, call_subcalls = 0;
+    // ---- CUDA-graph replay of the host-buffer entry point for launch-bound calls
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int nimg = 0; long long fcap = 0; bool want_f = false;
+                        long long gen = -1; int warm = 0; int n_nodes = 0; long long n_launch = 0; };
+    std::vector<GraphEntry> graphs;
+    // per-engine switches (umab_set_option "nosync" / "cuda_graphs"); defaults from UMAB_NOSYNC / UMAB_CUDA_GRAPHS
+    bool opt_nosync = [] { const char* e = getenv("UMAB_NOSYNC"); return !(e && atoi(e) == 0); }();
+    bool opt_graphs = [] { const char* e = getenv("UMAB_CUDA_GRAPHS"); return !(e && atoi(e) == 0); }();
+    bool nosync_enabled() const { return opt_nosync; }
+    bool graphs_enabled() const { return opt_graphs; }
+    long long graph_replays = 0, graph_captures = 0, overflow_retries = 0;
     std::vector<Chunk> chunks;
     bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
     static bool store_radial_enabled() {               // UMAB_STORE_RADIAL=0: recompute the radial MLP in the backward (A/B)
@@ -239,6 +269,28 @@ struct umab_engine {
     Prof prof;
     void* hp_pos = nullptr; void* hp_f = nullptr; void* hp_e = nullptr; size_t hp_cap = 0, hp_ecap = 0;
 
+    long long device_memory() {
+        if (!total_mem) {
+            size_t fr = 0, tot = 0;
+            UMAB_CUDA(cudaMemGetInfo(&fr, &tot));
+            total_mem = (long long)tot;
+        }
+        return total_mem;
+    }
+    // images one evaluation should take: bounded by the node state (~100 KB per atom) and, when forces are wanted, by
+    // the per-layer stores (so that the backward recomputes nothing); larger batches run as consecutive sub-batches
+    int images_per_call(bool forces, int nplanes) {
+        const long long max_atoms = 49152 / nplanes;
+        long long cap = std::max<long long>(1, max_atoms / std::max(n_atoms, 1));
+        if (forces && cfg.store_bytes >= 0) {
+            const double budget = cfg.store_bytes > 0 ? (double)cfg.store_bytes : 0.45 * (double)device_memory();
+            const double epi = hist_edges_per_image > 0 ? 1.03 * (double)hist_edges_per_image : 85.0 * n_atoms;
+            const double per_image = epi * (store_radial_enabled() ? STORE_FLOATS : YW + ZW) * 4.0 * cfg.num_layers * nplanes;
+            const long long fit = (long long)(budget / per_image);
+            if (fit >= 1) cap = std::min(cap, fit);
+        }
+        return (int)cap;
+    }
     template <class F> void timed(int cat, double work, cudaStream_t st, F&& f, double bytes = -1.0) {
         if (!prof.on) { f(); return; }
         Prof::Rec r{cat, prof.get(), prof.get(), work, bytes < 0 ? work : bytes};
@@ -384,7 +436,8 @@ struct umab_engine {
     }
 
     // ------------------------------------------------------------------ graph
-    void build_graph(const float* pos, int nimg, cudaStream_t st) {
+    // fcap > 0: sync-free build on edge arrays of that capacity (see the members above); 0: read row_ptr back
+    void build_graph(const float* pos, int nimg, cudaStream_t st, long long fcap = 0) {
         if (n_atoms <= 0) throw CudaError("umab_set_system has not been called");
         if (nimg <= 0) throw CudaError("n_images must be positive");
         n_img = nimg;
@@ -411,36 +464,95 @@ struct umab_engine {
             launch_neighbor_count(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, deg.i(), thr.f(), st);
         }
         launch_scan(deg.i(), row_ptr.i(), n_nodes, st);
-        size_t need = sizeof(int) * (n_nodes + 1);
-        if (need > h_pinned_cap) {
-            if (h_pinned) cudaFreeHost(h_pinned);
-            UMAB_CUDA(cudaMallocHost(&h_pinned, need + need / 4));
-            h_pinned_cap = need + need / 4;
+        fast_graph = fcap > 0;
+        const int* n_edges_dev = nullptr;
+        if (fast_graph) {
+            n_edges = fcap;
+            n_edges_dev = row_ptr.i() + n_nodes;
+            status_dev.ensure(2 * sizeof(int));
+            launch_edge_status(n_edges_dev, (int)fcap, status_dev.i(), st);
+        } else {
+            size_t need = sizeof(int) * (n_nodes + 1);
+            if (need > h_pinned_cap) {
+                if (h_pinned) cudaFreeHost(h_pinned);
+                UMAB_CUDA(cudaMallocHost(&h_pinned, need + need / 4));
+                h_pinned_cap = need + need / 4;
+                ++g_alloc_gen;
+            }
+            UMAB_CUDA(cudaMemcpyAsync(h_pinned, row_ptr.p, need, cudaMemcpyDeviceToHost, st));
+            UMAB_CUDA(cudaStreamSynchronize(st));
+            n_edges = h_pinned[n_nodes];
+            n_edges_actual = n_edges;
+            hist_edges_per_image = std::max<long long>(hist_edges_per_image, (n_edges + nimg - 1) / nimg);
         }
-        UMAB_CUDA(cudaMemcpyAsync(h_pinned, row_ptr.p, need, cudaMemcpyDeviceToHost, st));
-        UMAB_CUDA(cudaStreamSynchronize(st));
-        n_edges = h_pinned[n_nodes];
         if (n_edges > 0x7fffffffLL / 40) throw CudaError("too many edges in one batch: split it on the host");
         size_t ne = (size_t)std::max<long long>(n_edges, 1);
         src.ensure(sizeof(int) * ne); tgt.ensure(sizeof(int) * ne);
+        if (fast_graph) {          // padding rows [actual, capacity) must hold valid node indices
+            UMAB_CUDA(cudaMemsetAsync(src.p, 0, sizeof(int) * ne, st));
+            UMAB_CUDA(cudaMemsetAsync(tgt.p, 0, sizeof(int) * ne, st));
+        }
         if (cells)
             launch_neighbor_cell_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, cap_cells, cgrid.p, cstart.i(),
-                                      catoms.i(), thr.f(), row_ptr.i(), src.i(), tgt.i(), st);
+                                      catoms.i(), thr.f(), row_ptr.i(), src.i(), tgt.i(), (int)ne, st);
         else
-            launch_neighbor_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, thr.f(), row_ptr.i(), src.i(), tgt.i(), st);
+            launch_neighbor_fill(pos, nimg, n_atoms, cfg.cutoff, cfg.max_neighbors, thr.f(), row_ptr.i(), src.i(), tgt.i(),
+                                 (int)ne, st);
         odeg.ensure(sizeof(int) * n_nodes); sptr.ensure(sizeof(int) * (n_nodes + 1)); cursor.ensure(sizeof(int) * n_nodes);
         stmp.ensure(sizeof(int) * ne); sedge.ensure(sizeof(int) * ne);
-        launch_source_csr(src.i(), (int)n_edges, n_nodes, odeg.i(), sptr.i(), cursor.i(), stmp.i(), sedge.i(), st);
+        launch_source_csr(src.i(), (int)n_edges, n_edges_dev, n_nodes, odeg.i(), sptr.i(), cursor.i(), stmp.i(), sedge.i(), st);
+    }
+
+    // edges one chunk of the workspace can hold (worst case: the backward recomputes)
+    template <class S> long long chunk_capacity(bool extra) const {
+        const long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (28LL << 30);   // one 10k-atom image (~0.8 M edges) stays a closed chunk
+        const size_t per_edge = EDGE_WS_FLOATS + (extra ? EDGE_WS_EXTRA_RECOMPUTE : 0);
+        return std::max<long long>(budget / (long long)(per_edge * 4 * planes<S>()), 1024);
+    }
+    // capacity of the sync-free build for `nimg` images, or 0 when this call must read the edge count back: debug /
+    // profiling runs, no history yet for images of >= 128 atoms, or more edges than ONE chunk of the workspace holds
+    bool allow_fast = true;                            // false inside a call that runs as several sub-batches
+    template <class S> long long fast_capacity(int nimg) const {
+        if (!nosync_enabled() || !allow_fast || cfg.debug || prof.on || n_atoms < 2) return 0;
+        const long long complete = (long long)n_atoms * (n_atoms - 1);
+        long long per;
+        if (n_atoms < 128) per = complete;
+        else if (hist_edges_per_image > 0) per = std::min(complete, hist_edges_per_image + hist_edges_per_image / 32 + 64);
+        else return 0;
+        const long long tot = per * nimg;
+        return tot <= chunk_capacity<S>(true) ? tot : 0;
+    }
+    // collect {actual edge count, overflow} of a sync-free evaluation; true = the capacity was exceeded (results invalid:
+    // repeat the call -- the history now knows the larger count)
+    bool resolve_status() {
+        if (!status_pending) return false;
+        status_pending = false;
+        UMAB_CUDA(cudaEventSynchronize(status_ev));
+        n_edges_actual = h_status[0];
+        hist_edges_per_image = std::max<long long>(hist_edges_per_image, (n_edges_actual + status_nimg - 1) / std::max(status_nimg, 1));
+        return h_status[1] != 0;
+    }
+    void enqueue_status(cudaStream_t st, bool record_event) {
+        if (!h_status) { UMAB_CUDA(cudaMallocHost(&h_status, 2 * sizeof(int))); ++g_alloc_gen; }
+        if (!status_ev) UMAB_CUDA(cudaEventCreateWithFlags(&status_ev, cudaEventDisableTiming));
+        UMAB_CUDA(cudaMemcpyAsync(h_status, status_dev.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (record_event) UMAB_CUDA(cudaEventRecord(status_ev, st));
+        status_nimg = n_img;
     }
 
     template <class S> void plan_chunks() {
-        long long budget = cfg.workspace_bytes > 0 ? cfg.workspace_bytes : (28LL << 30);   // one 10k-atom image (~0.8 M edges) stays a closed chunk
         const bool extra = want_adjoint && !store_mode;
-        const size_t per_edge = EDGE_WS_FLOATS + (extra ? EDGE_WS_EXTRA_RECOMPUTE : 0);
-        long long cap = std::max<long long>(budget / (long long)(per_edge * 4 * planes<S>()), 1024);
+        long long cap = chunk_capacity<S>(extra);
         chunks.clear();
         int node0 = 0;
         long long biggest = 0;
+        if (fast_graph) {          // one closed chunk over the whole capacity (fast_capacity checked that it fits)
+            chunks.push_back(Chunk{0, n_nodes, 0, (int)n_edges});
+            chunks_closed = closed_chunks_enabled();
+            if (!chunks_closed) throw CudaError("UMAB_CLOSED_CHUNKS=0 needs UMAB_NOSYNC=0");
+            biggest = n_edges;
+            node0 = n_nodes;
+        } else {
         // closed chunks = whole images: every out-edge of a node of the chunk is an edge of the chunk, so the adjoint
         // can reduce the source halves by source node inside the chunk (no per-edge G buffer, no source_reduce pass)
         long long max_img = 0;
@@ -459,6 +571,7 @@ struct umab_engine {
                 b0 = b1;
             }
             node0 = n_nodes;
+        }
         }
         while (node0 < n_nodes) {
             long long e0 = h_pinned[node0];
@@ -611,10 +724,43 @@ struct umab_engine {
     // ------------------------------------------------------------------ full evaluation
     // S = float: energies + forces.  S = D1: positions carry a tangent (displacement direction);
     // forces.d then is d(forces)/d(eps) = -H.t, one analytic Hessian column per image.
+    bool capturing = false;                            // inside cudaStreamBeginCapture / EndCapture
     template <class S>
     void evaluate(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
+        evaluate_impl<S>(pos, nimg, energy_dev, forces, st);
+        if (fast_graph) {
+            enqueue_status(st, !capturing);
+            status_pending = !capturing;
+        }
+        call_images += nimg; call_subcalls += 1;
+    }
+    // a whole public call: sub-batches sized by images_per_call
+    template <class S>
+    void evaluate_batched(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
+        call_images = 0; call_edges = 0; call_subcalls = 0;
+        const long long stride = (long long)n_atoms * 3;
+        int s0 = 0;
+        allow_fast = images_per_call((bool)forces, planes<S>()) >= nimg;
+        struct Restore { bool& f; ~Restore() { f = true; } } restore{allow_fast};
+        while (s0 < nimg) {
+            const int step = std::max(1, images_per_call((bool)forces, planes<S>()));
+            const int nb = std::min(step, nimg - s0);
+            GP<S> p = pos, f = forces;
+            offset_gp(p, s0 * stride);
+            if (forces) offset_gp(f, s0 * stride);
+            evaluate<S>(p, nb, energy_dev ? energy_dev + s0 : nullptr, f, st);
+            if (!fast_graph) call_edges += n_edges;
+            s0 += nb;
+        }
+    }
+    static void offset_gp(GP<float>& g, long long off) { g.p += off; }
+    static void offset_gp(GP<D1>& g, long long off) { g.v += off; g.d += off; }
+    template <class S>
+    void evaluate_impl(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
         if (!finalized) throw CudaError("umab_finalize_weights has not been called");
-        timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(plane(pos, 0), nimg, st); });
+        if (resolve_status()) { /* an unchecked overflow of an earlier device-pointer call: the history has been updated */ }
+        const long long fcap = fast_capacity<S>(nimg);
+        timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(plane(pos, 0), nimg, st, fcap); });
         const int L = cfg.num_layers;
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
@@ -623,11 +769,7 @@ struct umab_engine {
         {
             const double need = (double)n_edges * (store_radial_enabled() ? STORE_FLOATS : YW + ZW) * 4.0 * L * planes<S>();
             double budget = (double)cfg.store_bytes;
-            if (cfg.store_bytes == 0) {
-                size_t fr = 0, tot = 0;
-                UMAB_CUDA(cudaMemGetInfo(&fr, &tot));
-                budget = 0.45 * (double)tot;
-            }
+            if (cfg.store_bytes == 0) budget = 0.45 * (double)device_memory();
             store_mode = want_f && cfg.store_bytes >= 0 && need <= budget;
             if (store_mode) {
                 ystore.resize(L); zstore.resize(L); rstore.resize(L); u1store.resize(L); u2store.resize(L);
@@ -756,7 +898,15 @@ struct umab_engine {
             launch_force_reduce(plane(gp<S>(g_vec), k), row_ptr.i(), sptr.i(), sedge.i(), n_nodes, plane(forces, k), st);
     }
 
+    void drop_graphs() {
+        for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
     ~umab_engine() {
+        drop_graphs();
+        if (status_ev) cudaEventDestroy(status_ev);
+        if (h_status) cudaFreeHost(h_status);
+        status_dev.release();
         tc_cache_destroy(tc_cache);
         tc2_cache_destroy(tc2_cache);
         for (auto& kv : weights) kv.second.buf.release();
@@ -863,6 +1013,11 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
     if (n == "neighbor_mode") {
         if (value < 0 || value > 2) throw CudaError("neighbor_mode: 0 auto, 1 brute force, 2 cell list");
         e->neighbor_mode = (int)value;
+    } else if (n == "nosync") {
+        e->opt_nosync = value != 0;
+    } else if (n == "cuda_graphs") {
+        e->opt_graphs = value != 0;
+        if (!e->opt_graphs) e->drop_graphs();
     } else if (n == "simt_round_fwd" || n == "simt_round_bwd") {
         // precision study: operand rounding emulated by the fp32 SIMT GEMM (GemmArgs::round_mode), forward / adjoint GEMMs
         if (value < 0 || value > 4) throw CudaError("simt_round_*: 0 exact, 1 tf32, 2 bf16x2 (W bf16), 3 bf16x2 (A bf16), 4 bf16");
@@ -870,6 +1025,21 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
     } else {
         throw CudaError("unknown option: " + n);
     }
+    UMAB_CATCH
+}
+
+int32_t umab_get_option(umab_engine* e, const char* name, int64_t* value) {
+    UMAB_TRY
+    if (!e || !name || !value) throw CudaError("null argument");
+    const std::string n(name);
+    if (n == "nosync") *value = e->opt_nosync;
+    else if (n == "cuda_graphs") *value = e->opt_graphs;
+    else if (n == "graph_replays") *value = e->graph_replays;
+    else if (n == "graph_captures") *value = e->graph_captures;
+    else if (n == "overflow_retries") *value = e->overflow_retries;
+    else if (n == "edges_per_image_seen") *value = e->hist_edges_per_image;
+    else if (n == "neighbor_mode") *value = e->neighbor_mode;
+    else throw CudaError("unknown option: " + n);
     UMAB_CATCH
 }
 
@@ -886,7 +1056,8 @@ int32_t umab_graph_counts(umab_engine* e, int64_t* n_nodes, int64_t* n_edges) {
     UMAB_TRY
     if (!e) throw CudaError("null argument");
     if (n_nodes) *n_nodes = e->n_nodes;
-    if (n_edges) *n_edges = e->n_edges;
+    // sync-free evaluations: the edge arrays are capacity-sized; report the actual count once it has been collected
+    if (n_edges) *n_edges = (e->fast_graph && !e->status_pending) ? e->n_edges_actual : e->n_edges;
     UMAB_CATCH
 }
 
@@ -906,8 +1077,26 @@ int32_t umab_energy_forces(umab_engine* e, const float* pos_dev, int32_t n_image
     UMAB_TRY
     if (!e || !pos_dev || !energy_dev) throw CudaError("null argument");
     DeviceGuard guard(e->cfg.device);
-    e->evaluate<float>(gpf(pos_dev), n_images, energy_dev, GP<float>{forces_dev}, (cudaStream_t)stream);
+    e->evaluate_batched<float>(gpf(pos_dev), n_images, energy_dev, GP<float>{forces_dev}, (cudaStream_t)stream);
     UMAB_CATCH
+}
+
+int32_t umab_last_call(umab_engine* e, int64_t* n_images, int64_t* n_edges, int64_t* n_subcalls) {
+    if (!e) { g_last_error = "null argument"; return 1; }
+    try {
+        DeviceGuard guard(e->cfg.device);
+        const bool was_pending = e->status_pending;
+        const bool overflow = e->resolve_status();
+        if (was_pending) e->call_edges += e->n_edges_actual;
+        if (n_images) *n_images = e->call_images;
+        if (n_edges) *n_edges = e->call_edges;
+        if (n_subcalls) *n_subcalls = e->call_subcalls;
+        if (overflow) {
+            g_last_error = "edge capacity exceeded in the last sync-free call: its results are invalid, repeat the call";
+            return UMAB_RETRY;
+        }
+    } catch (const std::exception& ex) { g_last_error = ex.what(); return 1; }
+    return 0;
 }
 
 int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n_images, double* energy_host,
@@ -915,6 +1104,7 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
     UMAB_TRY
     if (!e || !pos_host || !energy_host) throw CudaError("null argument");
     if (e->n_atoms <= 0) throw CudaError("umab_set_system has not been called");
+    if (n_images <= 0) throw CudaError("n_images must be positive");
     DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     size_t nb = (size_t)n_images * e->n_atoms * 3 * sizeof(float);
@@ -928,19 +1118,93 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
         UMAB_CUDA(cudaMallocHost(&e->hp_pos, nb + nb / 4));
         UMAB_CUDA(cudaMallocHost(&e->hp_f, nb + nb / 4));
         e->hp_cap = nb + nb / 4;
+        ++g_alloc_gen;
     }
     if (sizeof(double) * n_images > e->hp_ecap) {
         if (e->hp_e) cudaFreeHost(e->hp_e);
         UMAB_CUDA(cudaMallocHost(&e->hp_e, sizeof(double) * n_images * 2));
         e->hp_ecap = sizeof(double) * n_images * 2;
+        ++g_alloc_gen;
     }
     memcpy(e->hp_pos, pos_host, nb);
-    UMAB_CUDA(cudaMemcpyAsync(e->pos_own.p, e->hp_pos, nb, cudaMemcpyHostToDevice, st));
-    e->evaluate<float>(GP<float>{e->pos_own.f()}, n_images, e->e_dev.as<double>(),
-                       GP<float>{forces_host ? e->f_dev.f() : nullptr}, st);
-    UMAB_CUDA(cudaMemcpyAsync(e->hp_e, e->e_dev.p, sizeof(double) * n_images, cudaMemcpyDeviceToHost, st));
-    if (forces_host) UMAB_CUDA(cudaMemcpyAsync(e->hp_f, e->f_dev.p, nb, cudaMemcpyDeviceToHost, st));
-    UMAB_CUDA(cudaStreamSynchronize(st));
+    const bool want_f = forces_host != nullptr;
+    auto enqueue_all = [&] {
+        UMAB_CUDA(cudaMemcpyAsync(e->pos_own.p, e->hp_pos, nb, cudaMemcpyHostToDevice, st));
+        e->evaluate_batched<float>(GP<float>{e->pos_own.f()}, n_images, e->e_dev.as<double>(),
+                                   GP<float>{want_f ? e->f_dev.f() : nullptr}, st);
+        UMAB_CUDA(cudaMemcpyAsync(e->hp_e, e->e_dev.p, sizeof(double) * n_images, cudaMemcpyDeviceToHost, st));
+        if (want_f) UMAB_CUDA(cudaMemcpyAsync(e->hp_f, e->f_dev.p, nb, cudaMemcpyDeviceToHost, st));
+    };
+    for (int attempt = 0;; ++attempt) {
+        // launch-bound calls (one sub-batch, one chunk, sync-free graph build): the whole enqueue sequence -- H2D, ~200-700
+        // kernel launches, D2H -- is captured once per (images, capacity) and replayed as ONE cudaGraphLaunch
+        e->resolve_status();
+        const bool one = e->images_per_call(want_f, 1) >= n_images;
+        const long long fcap = one ? e->fast_capacity<float>(n_images) : 0;
+        umab_engine::GraphEntry* ge = nullptr;
+        if (fcap > 0 && e->graphs_enabled()) {
+            for (auto& g : e->graphs) if (g.nimg == n_images && g.fcap == fcap && g.want_f == want_f) ge = &g;
+            if (!ge) {
+                if (e->graphs.size() >= 16) e->drop_graphs();
+                e->graphs.push_back(umab_engine::GraphEntry{});
+                ge = &e->graphs.back();
+                ge->nimg = n_images; ge->fcap = fcap; ge->want_f = want_f;
+            }
+            if (ge->gen != g_alloc_gen.load()) {          // a buffer moved since: the captured addresses are stale
+                if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
+                ge->warm = 0;
+            }
+        }
+        bool launched = false;
+        if (ge && ge->exec) {
+            UMAB_CUDA(cudaGraphLaunch(ge->exec, st));
+            ++e->graph_replays;
+            g_launch_count += ge->n_launch;            // the kernels of the replayed graph
+            e->n_img = n_images; e->n_nodes = ge->n_nodes; e->n_edges = fcap; e->fast_graph = true;
+            e->call_images = n_images; e->call_edges = 0; e->call_subcalls = 1;
+            launched = true;
+        } else if (ge && ge->warm >= 1) {
+            // second call with stable buffers: capture.  Anything unexpected (an allocation, a sync) fails the capture;
+            // the call then simply runs un-captured.
+            cudaGraph_t graph = nullptr;
+            const long long launches0 = g_launch_count.load();
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                e->capturing = true;
+                try { enqueue_all(); } catch (...) { ok = false; }
+                e->capturing = false;
+                if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+            }
+            if (ok && e->fast_graph && ge->gen == g_alloc_gen.load() &&
+                cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {
+                ge->n_nodes = e->n_nodes;
+                ge->n_launch = g_launch_count.load() - launches0;
+                UMAB_CUDA(cudaGraphLaunch(ge->exec, st));
+                ++e->graph_captures;
+                launched = true;
+            } else {
+                cudaGetLastError();
+                ge->exec = nullptr; ge->warm = -1000000;       // never try again for this key
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (!launched) {
+            enqueue_all();
+            if (ge) { ge->warm += 1; ge->gen = g_alloc_gen.load(); }
+        }
+        UMAB_CUDA(cudaStreamSynchronize(st));
+        bool overflow = false;
+        if (e->fast_graph) {                 // the status words were copied by the same stream: valid after the sync
+            e->status_pending = false;
+            e->n_edges_actual = e->h_status[0];
+            e->hist_edges_per_image = std::max<long long>(e->hist_edges_per_image, (e->n_edges_actual + n_images - 1) / n_images);
+            e->call_edges += e->n_edges_actual;
+            overflow = e->h_status[1] != 0;
+        }
+        if (!overflow) break;
+        ++e->overflow_retries;
+        if (attempt >= 3) throw CudaError("edge capacity exceeded repeatedly");
+    }
     memcpy(energy_host, e->hp_e, sizeof(double) * n_images);
     if (forces_host) memcpy(forces_host, e->hp_f, nb);
     UMAB_CATCH
@@ -956,8 +1220,8 @@ int32_t umab_forces_jvp(umab_engine* e, const float* pos_dev, const float* tange
         e->f_dev.ensure((size_t)n_images * e->n_atoms * 3 * sizeof(float));
         forces_dev = e->f_dev.f();
     }
-    e->evaluate<D1>(GP<D1>{const_cast<float*>(pos_dev), const_cast<float*>(tangent_dev)}, n_images, energy_dev,
-                    GP<D1>{forces_dev, dforces_dev}, st);
+    e->evaluate_batched<D1>(GP<D1>{const_cast<float*>(pos_dev), const_cast<float*>(tangent_dev)}, n_images, energy_dev,
+                            GP<D1>{forces_dev, dforces_dev}, st);
     UMAB_CATCH
 }
 

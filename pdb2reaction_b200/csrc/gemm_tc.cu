@@ -421,7 +421,7 @@ void tc_cache_destroy(TcPlaneCache* c) { delete c; }
 void tc_cache_clear(TcPlaneCache* c) { if (c) c->clear(); }
 
 bool gemm_tc_supported(const GemmArgs& a) {
-    return a.batch == 1 && a.M >= 256 && a.K % BK == 0 && a.K >= BK && a.N % 32 == 0 && pick_bn(a.N) >= 32 &&
+    return a.batch == 1 && a.M >= 1 && a.K % BK == 0 && a.K >= BK && a.N % 32 == 0 && pick_bn(a.N) >= 32 &&
            a.lda % 4 == 0 && a.ldc % 4 == 0 && a.ldw == a.K;
 }
 

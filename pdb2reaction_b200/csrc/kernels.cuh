@@ -8,7 +8,7 @@ namespace umab {
 // ---- neighbors.cu
 void launch_neighbor_count(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int* deg, float* thr, cudaStream_t st);
 void launch_neighbor_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, const float* thr,
-                          const int* row_ptr, int* src, int* tgt, cudaStream_t st);
+                          const int* row_ptr, int* src, int* tgt, int e_cap, cudaStream_t st);
 void launch_scan(const int* in, int* out, int n, cudaStream_t st);
 // shared-memory cell-list search (same edge list as the brute-force kernels)
 size_t cell_grid_bytes();
@@ -19,9 +19,10 @@ void launch_neighbor_cell_count(const float* pos, int n_img, int n_atoms, float 
                                 cudaStream_t st);
 void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int cap_cells,
                                const void* grid, const int* cell_start, const int* cell_atoms, const float* thr,
-                               const int* row_ptr, int* src, int* tgt, cudaStream_t st);
-void launch_source_csr(const int* src, int n_edges, int n_nodes, int* odeg, int* sptr, int* cursor, int* tmp,
-                       int* sedge, cudaStream_t st);
+                               const int* row_ptr, int* src, int* tgt, int e_cap, cudaStream_t st);
+void launch_edge_status(const int* total_dev, int e_cap, int* status_dev, cudaStream_t st);
+void launch_source_csr(const int* src, int n_edges, const int* n_edges_dev, int n_nodes, int* odeg, int* sptr, int* cursor,
+                       int* tmp, int* sedge, cudaStream_t st);
 
 // ---- geometry.cu
 template <class S>

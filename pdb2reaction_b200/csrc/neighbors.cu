@@ -38,7 +38,7 @@ template <int MODE>
 __global__ void __launch_bounds__(WARPS * 32)
 neighbor_kernel(const float* __restrict__ pos, int n_atoms, float rc2, int cap,
                 int* __restrict__ deg, float* __restrict__ thr,
-                const int* __restrict__ row_ptr, int* __restrict__ src, int* __restrict__ tgt) {
+                const int* __restrict__ row_ptr, int* __restrict__ src, int* __restrict__ tgt, int e_cap) {
     __shared__ float sx[TILE], sy[TILE], sz[TILE];
     const int img = blockIdx.y;
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -72,8 +72,10 @@ neighbor_kernel(const float* __restrict__ pos, int n_atoms, float rc2, int cap,
             unsigned m = __ballot_sync(0xffffffffu, keep);
             if (MODE == 1 && keep) {
                 int o = out + count + __popc(m & ((1u << lane) - 1u));
-                src[o] = (int)base + s0 + q;
-                tgt[o] = (int)base + t_local;
+                if (o < e_cap) {           // capacity-sized edge arrays (sync-free path): an overflow is flagged, never written
+                    src[o] = (int)base + s0 + q;
+                    tgt[o] = (int)base + t_local;
+                }
             }
             count += __popc(m);
         }
@@ -135,14 +137,24 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, 
     if (t == 1023) out[n] = part[1023];
 }
 
-__global__ void out_degree_kernel(const int* __restrict__ src, int n_edges, int* __restrict__ odeg) {
+// n_edges = launch bound (capacity of the edge arrays); n_dev (nullable) = the actual edge count on the device
+__global__ void out_degree_kernel(const int* __restrict__ src, int n_edges, const int* __restrict__ n_dev,
+                                  int* __restrict__ odeg) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n_edges = min(n_edges, *n_dev);
     if (e < n_edges) atomicAdd(&odeg[src[e]], 1);
 }
 
-__global__ void out_fill_kernel(const int* __restrict__ src, int n_edges, const int* __restrict__ sptr,
-                                int* __restrict__ cursor, int* __restrict__ sedge_tmp) {
+// {actual edge count, overflow flag} of a capacity-sized graph build
+__global__ void edge_status_kernel(const int* __restrict__ total, int e_cap, int* __restrict__ status) {
+    status[0] = *total;
+    status[1] = *total > e_cap ? 1 : 0;
+}
+
+__global__ void out_fill_kernel(const int* __restrict__ src, int n_edges, const int* __restrict__ n_dev,
+                                const int* __restrict__ sptr, int* __restrict__ cursor, int* __restrict__ sedge_tmp) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n_edges = min(n_edges, *n_dev);
     if (e < n_edges) {
         int j = src[e];
         int o = atomicAdd(&cursor[j], 1);
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 neighbor_cell_kernel(const float* __restrict__ pos, int n_atoms, float rc2, int cap_nb, int cap_cells,
                      const CellGrid* __restrict__ grid, const int* __restrict__ cell_start,
                      const int* __restrict__ cell_atoms, int* __restrict__ deg, float* __restrict__ thr,
-                     const int* __restrict__ row_ptr, int* __restrict__ src, int* __restrict__ tgt) {
+                     const int* __restrict__ row_ptr, int* __restrict__ src, int* __restrict__ tgt, int e_cap) {
     extern __shared__ unsigned bitmap[];                       // MODE 1: WARPS x ceil(n_atoms / 32) words
     __shared__ float sx[TILE], sy[TILE], sz[TILE];
     __shared__ int sid[TILE];
@@ -411,8 +423,10 @@ neighbor_cell_kernel(const float* __restrict__ pos, int n_atoms, float rc2, int 
                 while (b2) {
                     const int bit = __ffs(b2) - 1;
                     b2 &= b2 - 1u;
-                    src[o] = (int)base + w * 32 + bit;
-                    tgt[o] = (int)base + t_local;
+                    if (o < e_cap) {
+                        src[o] = (int)base + w * 32 + bit;
+                        tgt[o] = (int)base + t_local;
+                    }
                     ++o;
                 }
                 out += __shfl_sync(0xffffffffu, incl, 31);
@@ -446,13 +460,13 @@ void launch_neighbor_cell_count(const float* pos, int n_img, int n_atoms, float 
     dim3 g(cap_cells, n_img);
     neighbor_cell_kernel<0><<<g, WARPS * 32, 0, st>>>(pos, n_atoms, cutoff * cutoff, cap, cap_cells,
                                                       reinterpret_cast<const CellGrid*>(grid), cell_start, cell_atoms, deg,
-                                                      thr, nullptr, nullptr, nullptr);
+                                                      thr, nullptr, nullptr, nullptr, 0);
     UMAB_LAUNCH_CHECK();
 }
 
 void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int cap_cells,
                                const void* grid, const int* cell_start, const int* cell_atoms, const float* thr,
-                               const int* row_ptr, int* src, int* tgt, cudaStream_t st) {
+                               const int* row_ptr, int* src, int* tgt, int e_cap, cudaStream_t st) {
     dim3 g(cap_cells, n_img);
     const size_t smem = (size_t)WARPS * ((n_atoms + 31) / 32) * sizeof(unsigned);
     // the opt-in above 48 KB is a per-device attribute; engines on several GPUs run on their own host threads
@@ -470,7 +484,7 @@ void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float c
     }
     neighbor_cell_kernel<1><<<g, WARPS * 32, smem, st>>>(pos, n_atoms, cutoff * cutoff, cap, cap_cells,
                                                          reinterpret_cast<const CellGrid*>(grid), cell_start, cell_atoms,
-                                                         nullptr, const_cast<float*>(thr), row_ptr, src, tgt);
+                                                         nullptr, const_cast<float*>(thr), row_ptr, src, tgt, e_cap);
     UMAB_LAUNCH_CHECK();
 }
 
@@ -478,15 +492,15 @@ void launch_neighbor_count(const float* pos, int n_img, int n_atoms, float cutof
                            int* deg, float* thr, cudaStream_t st) {
     dim3 grid((n_atoms + WARPS - 1) / WARPS, n_img);
     neighbor_kernel<0><<<grid, WARPS * 32, 0, st>>>(pos, n_atoms, cutoff * cutoff, cap, deg, thr,
-                                                    nullptr, nullptr, nullptr);
+                                                    nullptr, nullptr, nullptr, 0);
     UMAB_LAUNCH_CHECK();
 }
 
 void launch_neighbor_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap,
-                          const float* thr, const int* row_ptr, int* src, int* tgt, cudaStream_t st) {
+                          const float* thr, const int* row_ptr, int* src, int* tgt, int e_cap, cudaStream_t st) {
     dim3 grid((n_atoms + WARPS - 1) / WARPS, n_img);
     neighbor_kernel<1><<<grid, WARPS * 32, 0, st>>>(pos, n_atoms, cutoff * cutoff, cap, nullptr,
-                                                    const_cast<float*>(thr), row_ptr, src, tgt);
+                                                    const_cast<float*>(thr), row_ptr, src, tgt, e_cap);
     UMAB_LAUNCH_CHECK();
 }
 
@@ -496,17 +510,23 @@ void launch_scan(const int* in, int* out, int n, cudaStream_t st) {
 }
 
 // by-source CSR: sptr [n_nodes+1], sedge [n_edges] (edge ids ascending within each source)
-void launch_source_csr(const int* src, int n_edges, int n_nodes, int* odeg, int* sptr, int* cursor,
+void launch_edge_status(const int* total_dev, int e_cap, int* status_dev, cudaStream_t st) {
+    edge_status_kernel<<<1, 1, 0, st>>>(total_dev, e_cap, status_dev);
+    UMAB_LAUNCH_CHECK();
+}
+
+// n_edges: launch bound (edge-array capacity); n_edges_dev (nullable): actual count on the device
+void launch_source_csr(const int* src, int n_edges, const int* n_edges_dev, int n_nodes, int* odeg, int* sptr, int* cursor,
                        int* tmp, int* sedge, cudaStream_t st) {
     UMAB_CUDA(cudaMemsetAsync(odeg, 0, sizeof(int) * n_nodes, st));
     UMAB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * n_nodes, st));
     if (n_edges > 0) {
-        out_degree_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(src, n_edges, odeg);
+        out_degree_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(src, n_edges, n_edges_dev, odeg);
         UMAB_LAUNCH_CHECK();
     }
     launch_scan(odeg, sptr, n_nodes, st);
     if (n_edges > 0) {
-        out_fill_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(src, n_edges, sptr, cursor, tmp);
+        out_fill_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(src, n_edges, n_edges_dev, sptr, cursor, tmp);
         UMAB_LAUNCH_CHECK();
         out_sort_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(sptr, tmp, sedge, n_nodes);
         UMAB_LAUNCH_CHECK();

@@ -20,7 +20,8 @@ from .arch import UMAArch
 _LIB_PATH = os.environ.get("UMAB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libumab.so")
 _lib = None
 
-ABI_VERSION = 6
+ABI_VERSION = 7
+UMAB_RETRY = 2          # umab_last_call: the sync-free graph build overflowed its edge capacity, repeat the call
 # "simt": fp32 FFMA GEMMs; "tc": tcgen05 bf16x3 tensor-core GEMMs; "auto": tc for images of >= 100 atoms
 DEFAULT_GEMM = "auto"
 GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
@@ -28,8 +29,8 @@ GEMM_MODES = {"simt": 0, "tc": 1, "auto": 2}
 # every symbol include/umab.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "umab_abi_version", "umab_last_error", "umab_create", "umab_destroy", "umab_set_weight",
-    "umab_finalize_weights", "umab_set_option", "umab_set_system", "umab_build_graph", "umab_graph_counts",
-    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
+    "umab_finalize_weights", "umab_set_option", "umab_get_option", "umab_set_system", "umab_build_graph", "umab_graph_counts",
+    "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_last_call", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
     "umab_hessian_fd_columns", "umab_hessian_mw_workspace", "umab_hessian_mw_project",
 )
@@ -77,9 +78,11 @@ def load_library(path: Optional[str] = None):
     lib.umab_graph_copy.argtypes = [vp, vp, vp, vp, vp]
     lib.umab_energy_forces.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.umab_energy_forces_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.umab_last_call.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.umab_forces_jvp.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     lib.umab_gemm.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.umab_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.umab_get_option.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
     lib.umab_gemm_bench.argtypes = [i32, vp, vp, vp, i64, i32, i32, i32, ctypes.POINTER(ctypes.c_double), vp]
     lib.umab_debug_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     lib.umab_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
@@ -230,6 +233,7 @@ class UmabEngine:
                               0.45 * torch.cuda.get_device_properties(self.device).total_memory)
         self._edges_per_atom = 85.0          # refined from the measured graphs
         self.last_call_edges = 0             # edges summed over the sub-batches of the last public call
+        self.last_call_subcalls = 0
 
     def images_per_call(self, forces: bool = True) -> int:
         """How many images one library call should take: bounded by the node state, and -- when
@@ -243,11 +247,6 @@ class UmabEngine:
             if fit >= 1:
                 cap = min(cap, fit)
         return cap
-
-    def _note_graph(self):
-        nn_, ne_ = self.graph_counts()
-        if nn_ > 0:
-            self._edges_per_atom = max(20.0, 1.03 * ne_ / nn_)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -263,27 +262,33 @@ class UmabEngine:
     def _stream_ptr(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _last_call(self) -> bool:
+        """Collect the last call's counters; False = its sync-free graph build overflowed (repeat the call)."""
+        ni, ne, ns = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        rc = self.lib.umab_last_call(self._h, ctypes.byref(ni), ctypes.byref(ne), ctypes.byref(ns))
+        if rc == UMAB_RETRY:
+            return False
+        _check(self.lib, rc)
+        self.last_call_edges, self.last_call_subcalls = ne.value, ns.value
+        if ni.value > 0 and ne.value > 0:
+            self._edges_per_atom = max(20.0, 1.03 * ne.value / (ni.value * self.n_atoms))
+        return True
+
     # ------------------------------------------------------------------ device-resident API
     def energy_forces(self, pos: torch.Tensor, forces: bool = True):
         """pos [B, N, 3] float32 CUDA tensor (Angstrom) -> (E [B] float64, F [B,N,3] float32 | None).
-        Large batches are passed to the library in sub-batches (``images_per_call``)."""
+        ONE library call; batches larger than the per-layer stores allow run as sub-batches inside it."""
         assert pos.is_cuda and pos.dtype == torch.float32 and pos.dim() == 3 and pos.shape[1] == self.n_atoms
         pos = pos.contiguous()
         b = pos.shape[0]
         e = torch.empty(b, dtype=torch.float64, device=pos.device)
         f = torch.empty_like(pos) if forces else None
-        step = self.images_per_call(forces)
-        s, self.last_call_edges = 0, 0
-        while s < b:
-            t = min(b, s + step)
-            _check(self.lib, self.lib.umab_energy_forces(self._h, pos[s:t].data_ptr(), t - s, e[s:t].data_ptr(),
-                                                         f[s:t].data_ptr() if forces else None, self._stream_ptr()))
-            self.last_call_edges += self.graph_counts()[1]
-            if s == 0:
-                self._note_graph()
-                step = self.images_per_call(forces)
-            s = t
-        return e, f
+        for _ in range(4):
+            _check(self.lib, self.lib.umab_energy_forces(self._h, pos.data_ptr(), b, e.data_ptr(),
+                                                         f.data_ptr() if forces else None, self._stream_ptr()))
+            if self._last_call():
+                return e, f
+        raise RuntimeError("umab: edge capacity exceeded repeatedly")
 
     # ------------------------------------------------------------------ host-buffer API (e2e path)
     def energy_forces_host(self, pos: np.ndarray, forces: bool = True):
@@ -293,18 +298,9 @@ class UmabEngine:
         b = pos.shape[0]
         e = np.empty(b, dtype=np.float64)
         f = np.empty_like(pos) if forces else None
-        step = self.images_per_call(forces)
-        s, self.last_call_edges = 0, 0
-        while s < b:
-            t = min(b, s + step)
-            _check(self.lib, self.lib.umab_energy_forces_host(self._h, pos[s:t].ctypes.data, t - s, e[s:t].ctypes.data,
-                                                              f[s:t].ctypes.data if forces else None,
-                                                              self._stream_ptr()))
-            self.last_call_edges += self.graph_counts()[1]
-            if s == 0:
-                self._note_graph()
-                step = self.images_per_call(forces)
-            s = t
+        _check(self.lib, self.lib.umab_energy_forces_host(self._h, pos.ctypes.data, b, e.ctypes.data,
+                                                          f.ctypes.data if forces else None, self._stream_ptr()))
+        self._last_call()
         return e, f
 
     # ------------------------------------------------------------------ analytic Hessian columns
@@ -318,12 +314,12 @@ class UmabEngine:
         b = pos.shape[0]
         f = torch.empty_like(pos)
         df = torch.empty_like(pos)
-        step = max(1, self.images_per_call(True) // 2)          # dual tensors: twice the memory per image
-        for s in range(0, b, step):
-            t = min(b, s + step)
-            _check(self.lib, self.lib.umab_forces_jvp(self._h, pos[s:t].data_ptr(), tangent[s:t].data_ptr(), t - s, None,
-                                                      f[s:t].data_ptr(), df[s:t].data_ptr(), self._stream_ptr()))
-        return f, df
+        for _ in range(4):
+            _check(self.lib, self.lib.umab_forces_jvp(self._h, pos.data_ptr(), tangent.data_ptr(), b, None,
+                                                      f.data_ptr(), df.data_ptr(), self._stream_ptr()))
+            if self._last_call():
+                return f, df
+        raise RuntimeError("umab: edge capacity exceeded repeatedly")
 
     def graph(self, pos: torch.Tensor):
         """Neighbour search only -> edge_index [2, E] int64 (row 0 source, row 1 target), CPU."""
@@ -343,6 +339,16 @@ class UmabEngine:
     def set_neighbor_mode(self, mode: str):
         """'auto' (shared-memory cell list from 128 atoms per image), 'brute' or 'cell'; identical edge lists."""
         _check(self.lib, self.lib.umab_set_option(self._h, b"neighbor_mode", self.NEIGHBOR_MODES[mode]))
+
+    def set_option(self, name: str, value: int):
+        """Run-time switches of include/umab.h: "nosync", "cuda_graphs", "neighbor_mode", ..."""
+        _check(self.lib, self.lib.umab_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        """Option values and counters: "graph_replays", "graph_captures", "overflow_retries", "edges_per_image_seen"."""
+        v = ctypes.c_int64()
+        _check(self.lib, self.lib.umab_get_option(self._h, name.encode(), ctypes.byref(v)))
+        return v.value
 
     def graph_counts(self):
         nn_, ne_ = ctypes.c_int64(), ctypes.c_int64()

@@ -175,7 +175,7 @@ struct DeviceGuard {
 
 constexpr int YW = 640 + 512 + 256;      // conv-1 outputs per edge: m=0 | m=1 (o_r|o_i) | m=2 (p_r|p_i)
 constexpr int ZW = 384 + 512 + 256;      // conv-2 outputs per edge
-constexpr size_t EDGE_WS_FLOATS = 2304 + YW + 1152 + ZW + 1536 + 4 * 128;   // 8064 per edge
+constexpr size_t EDGE_WS_FLOATS = 2304 + 1536 /* wY: max(YW, g_rad) */ + 1152 + ZW + 1536 + 4 * 128;   // 8192 per edge
 constexpr size_t EDGE_WS_EXTRA_RECOMPUTE = YW + ZW;
 constexpr int STORE_FLOATS = YW + ZW + 1536 + 2 * 128;   // per edge and layer in store mode: Y, Z, rad, u1, u2   // adjoint operands g_Y / g_Z when Y / Z live in the workspace
 
@@ -231,7 +231,7 @@ struct umab_engine {
     bool opt_graphs = [] { const char* e = getenv("UMAB_CUDA_GRAPHS"); return !(e && atoi(e) == 0); }();
     bool nosync_enabled() const { return opt_nosync; }
     bool graphs_enabled() const { return opt_graphs; }
-    long long graph_replays = 0, graph_captures = 0, overflow_retries = 0;
+    long long graph_replays = 0, graph_captures = 0, overflow_retries = 0, fast_calls = 0;
     std::vector<Chunk> chunks;
     bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
     static bool store_radial_enabled() {               // UMAB_STORE_RADIAL=0: recompute the radial MLP in the backward (A/B)
@@ -467,10 +467,11 @@ struct umab_engine {
         fast_graph = fcap > 0;
         const int* n_edges_dev = nullptr;
         if (fast_graph) {
+            ++fast_calls;
             n_edges = fcap;
             n_edges_dev = row_ptr.i() + n_nodes;
             status_dev.ensure(2 * sizeof(int));
-            launch_edge_status(n_edges_dev, (int)fcap, status_dev.i(), st);
+            launch_edge_status(row_ptr.i(), n_nodes, (int)fcap, status_dev.i(), st);
         } else {
             size_t need = sizeof(int) * (n_nodes + 1);
             if (need > h_pinned_cap) {
@@ -488,8 +489,10 @@ struct umab_engine {
         if (n_edges > 0x7fffffffLL / 40) throw CudaError("too many edges in one batch: split it on the host");
         size_t ne = (size_t)std::max<long long>(n_edges, 1);
         src.ensure(sizeof(int) * ne); tgt.ensure(sizeof(int) * ne);
-        if (fast_graph) {          // padding rows [actual, capacity) must hold valid node indices
-            UMAB_CUDA(cudaMemsetAsync(src.p, 0, sizeof(int) * ne, st));
+        if (fast_graph) {
+            // padding rows [actual, capacity) must hold valid node indices; source 1 -> target 0 is a regular pair of
+            // distinct atoms (a self pair would have zero length: NaN Wigner blocks in the padding rows)
+            launch_fill_int(src.i(), (int)ne, 1, st);
             UMAB_CUDA(cudaMemsetAsync(tgt.p, 0, sizeof(int) * ne, st));
         }
         if (cells)
@@ -513,12 +516,19 @@ struct umab_engine {
     // profiling runs, no history yet for images of >= 128 atoms, or more edges than ONE chunk of the workspace holds
     bool allow_fast = true;                            // false inside a call that runs as several sub-batches
     template <class S> long long fast_capacity(int nimg) const {
-        if (!nosync_enabled() || !allow_fast || cfg.debug || prof.on || n_atoms < 2) return 0;
+        static const bool debug_fast = getenv("UMAB_DEBUG_FAST") != nullptr;      // keep the debug tensors on the sync-free path
+        if (!nosync_enabled() || !allow_fast || (cfg.debug && !debug_fast) || prof.on || n_atoms < 2) return 0;
         const long long complete = (long long)n_atoms * (n_atoms - 1);
         long long per;
         if (n_atoms < 128) per = complete;
-        else if (hist_edges_per_image > 0) per = std::min(complete, hist_edges_per_image + hist_edges_per_image / 32 + 64);
-        else return 0;
+        else if (hist_edges_per_image > 0) {
+            // + 3 % head-room, rounded up to a 1/16-octave grid so that the capacity (= the key of the captured CUDA
+            // graphs and the shape of every launch) stays put while the geometry drifts
+            per = hist_edges_per_image + hist_edges_per_image / 32 + 64;
+            long long q = 1;
+            while ((q << 5) <= per) q <<= 1;              // q = 2^(floor(log2 per) - 4)
+            per = std::min(complete, (per + q - 1) / q * q);
+        } else return 0;
         const long long tot = per * nimg;
         return tot <= chunk_capacity<S>(true) ? tot : 0;
     }
@@ -585,7 +595,8 @@ struct umab_engine {
         }
         chunk_cap = std::max<long long>(biggest, 1);
         size_t f = sizeof(float) * (size_t)chunk_cap;
-        wA.ensure<S>(f * 2304); wY.ensure<S>(f * YW); wB.ensure<S>(f * 1152); wZ.ensure<S>(f * ZW);
+        // wY also holds g_rad [n_e, 1536] in store mode (bufs_for: b.grad), which is wider than Y [n_e, 1408]
+        wA.ensure<S>(f * 2304); wY.ensure<S>(f * std::max(YW, 1536)); wB.ensure<S>(f * 1152); wZ.ensure<S>(f * ZW);
         wRAD.ensure<S>(f * 1536);
         wU1.ensure<S>(f * 128); wH1.ensure<S>(f * 128); wU2.ensure<S>(f * 128); wH2.ensure<S>(f * 128);
         if (extra) { wGY.ensure<S>(f * std::max(YW, 1536)); wGZ.ensure<S>(f * ZW); }
@@ -725,6 +736,8 @@ struct umab_engine {
     // S = float: energies + forces.  S = D1: positions carry a tangent (displacement direction);
     // forces.d then is d(forces)/d(eps) = -H.t, one analytic Hessian column per image.
     bool capturing = false;                            // inside cudaStreamBeginCapture / EndCapture
+    cudaStream_t own_stream = nullptr;                 // host-buffer calls issued on the legacy default stream run here
+    cudaEvent_t order_ev = nullptr;
     template <class S>
     void evaluate(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
         evaluate_impl<S>(pos, nimg, energy_dev, forces, st);
@@ -904,6 +917,8 @@ struct umab_engine {
     }
     ~umab_engine() {
         drop_graphs();
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (order_ev) cudaEventDestroy(order_ev);
         if (status_ev) cudaEventDestroy(status_ev);
         if (h_status) cudaFreeHost(h_status);
         status_dev.release();
@@ -1037,6 +1052,7 @@ int32_t umab_get_option(umab_engine* e, const char* name, int64_t* value) {
     else if (n == "graph_replays") *value = e->graph_replays;
     else if (n == "graph_captures") *value = e->graph_captures;
     else if (n == "overflow_retries") *value = e->overflow_retries;
+    else if (n == "fast_calls") *value = e->fast_calls;
     else if (n == "edges_per_image_seen") *value = e->hist_edges_per_image;
     else if (n == "neighbor_mode") *value = e->neighbor_mode;
     else throw CudaError("unknown option: " + n);
@@ -1107,6 +1123,17 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
     if (n_images <= 0) throw CudaError("n_images must be positive");
     DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (st == nullptr || st == cudaStreamLegacy) {
+        // the legacy default stream cannot be captured into a CUDA graph: host-buffer calls are self-contained, so they
+        // run on a stream of the engine, ordered after whatever the caller has queued on its stream so far
+        if (!e->own_stream) {
+            UMAB_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+            UMAB_CUDA(cudaEventCreateWithFlags(&e->order_ev, cudaEventDisableTiming));
+        }
+        UMAB_CUDA(cudaEventRecord(e->order_ev, st));
+        UMAB_CUDA(cudaStreamWaitEvent(e->own_stream, e->order_ev, 0));
+        st = e->own_stream;
+    }
     size_t nb = (size_t)n_images * e->n_atoms * 3 * sizeof(float);
     e->pos_own.ensure(nb);
     e->e_dev.ensure(sizeof(double) * n_images);
@@ -1168,12 +1195,22 @@ int32_t umab_energy_forces_host(umab_engine* e, const float* pos_host, int32_t n
             // the call then simply runs un-captured.
             cudaGraph_t graph = nullptr;
             const long long launches0 = g_launch_count.load();
-            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            static const bool dbg_graph = getenv("UMAB_DEBUG_GRAPH") != nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            bool ok = ce == cudaSuccess;
+            if (!ok && dbg_graph) fprintf(stderr, "umab: BeginCapture failed: %s\n", cudaGetErrorString(ce));
             if (ok) {
                 e->capturing = true;
-                try { enqueue_all(); } catch (...) { ok = false; }
+                try { enqueue_all(); } catch (const std::exception& ex) {
+                    ok = false;
+                    if (dbg_graph) fprintf(stderr, "umab: capture aborted: %s\n", ex.what());
+                }
                 e->capturing = false;
-                if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+                ce = cudaStreamEndCapture(st, &graph);
+                if (ce != cudaSuccess || !graph) {
+                    ok = false;
+                    if (dbg_graph) fprintf(stderr, "umab: EndCapture failed: %s\n", cudaGetErrorString(ce));
+                }
             }
             if (ok && e->fast_graph && ge->gen == g_alloc_gen.load() &&
                 cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess) {

@@ -20,7 +20,8 @@ void launch_neighbor_cell_count(const float* pos, int n_img, int n_atoms, float 
 void launch_neighbor_cell_fill(const float* pos, int n_img, int n_atoms, float cutoff, int cap, int cap_cells,
                                const void* grid, const int* cell_start, const int* cell_atoms, const float* thr,
                                const int* row_ptr, int* src, int* tgt, int e_cap, cudaStream_t st);
-void launch_edge_status(const int* total_dev, int e_cap, int* status_dev, cudaStream_t st);
+void launch_fill_int(int* p, int n, int v, cudaStream_t st);
+void launch_edge_status(int* row_ptr, int n_nodes, int e_cap, int* status_dev, cudaStream_t st);
 void launch_source_csr(const int* src, int n_edges, const int* n_edges_dev, int n_nodes, int* odeg, int* sptr, int* cursor,
                        int* tmp, int* sedge, cudaStream_t st);
 

@@ -150,6 +150,12 @@ __global__ void edge_status_kernel(const int* __restrict__ total, int e_cap, int
     status[0] = *total;
     status[1] = *total > e_cap ? 1 : 0;
 }
+// after an overflow every CSR walk must still stay inside the capacity-sized edge arrays (the results of such a call
+// are discarded and the call repeated): clamp the offsets
+__global__ void clamp_row_ptr_kernel(int* __restrict__ row_ptr, int n, int e_cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && row_ptr[i] > e_cap) row_ptr[i] = e_cap;
+}
 
 __global__ void out_fill_kernel(const int* __restrict__ src, int n_edges, const int* __restrict__ n_dev,
                                 const int* __restrict__ sptr, int* __restrict__ cursor, int* __restrict__ sedge_tmp) {
@@ -510,8 +516,20 @@ void launch_scan(const int* in, int* out, int n, cudaStream_t st) {
 }
 
 // by-source CSR: sptr [n_nodes+1], sedge [n_edges] (edge ids ascending within each source)
-void launch_edge_status(const int* total_dev, int e_cap, int* status_dev, cudaStream_t st) {
-    edge_status_kernel<<<1, 1, 0, st>>>(total_dev, e_cap, status_dev);
+__global__ void fill_int_kernel(int* __restrict__ p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill_int(int* p, int n, int v, cudaStream_t st) {
+    if (n <= 0) return;
+    fill_int_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, v);
+    UMAB_LAUNCH_CHECK();
+}
+
+void launch_edge_status(int* row_ptr, int n_nodes, int e_cap, int* status_dev, cudaStream_t st) {
+    edge_status_kernel<<<1, 1, 0, st>>>(row_ptr + n_nodes, e_cap, status_dev);
+    UMAB_LAUNCH_CHECK();
+    clamp_row_ptr_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, st>>>(row_ptr, n_nodes + 1, e_cap);
     UMAB_LAUNCH_CHECK();
 }
 

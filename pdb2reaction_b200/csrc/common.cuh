@@ -123,5 +123,7 @@ struct GemmArgs {
 };
 
 void gemm_simt(const GemmArgs& a, cudaStream_t st);
+// latency variant for small molecules: 64 x 64 tiles, split-K over a thread-block cluster (gemm_simt.cu)
+void gemm_simt_splitk(const GemmArgs& a, cudaStream_t st);
 
 }  // namespace umab

@@ -363,6 +363,10 @@ struct umab_engine {
     // gemm_mode 0: fp32 SIMT; 1: tcgen05 bf16x3; 2 (auto): tensor cores for images of >= 100 atoms.  The
     // choice depends on the image size only, never on the batch, so an image evaluated alone and
     // inside a batch goes through the same arithmetic.
+    static bool splitk_enabled() {
+        static const bool on = [] { const char* e = getenv("UMAB_SIMT_SPLITK"); return !(e && atoi(e) == 0); }();
+        return on;
+    }
     bool use_tc() const { return cfg.gemm_mode == 1 || (cfg.gemm_mode == 2 && n_atoms >= 100); }
     // precision study (set by umab_set_option "simt_round_fwd" / "simt_round_bwd"; SIMT path only)
     int simt_round_fwd = 0, simt_round_bwd = 0;
@@ -373,6 +377,7 @@ struct umab_engine {
         timed(P_GEMM, 2.0 * a.M * (double)a.N * a.K * a.batch, st, [&] {
             if (a.A_hi) gemm_tc2(a, st, tc2_cache, 0);
             else if (use_tc() && gemm_tc_supported(a)) gemm_tc(a, st, tc_cache);
+            else if (n_atoms < 100 && splitk_enabled()) gemm_simt_splitk(a, st);     // small molecules: launch-latency bound
             else gemm_simt(a, st);
         }, /* algorithmic bytes: A and C once (+C again when accumulating), W once */
            4.0 * a.batch * ((double)a.M * a.K + (double)a.M * a.N * (a.accumulate ? 2 : 1)) + 4.0 * a.N * (double)a.K);
@@ -1304,6 +1309,8 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
         // mode 2: planes cached by pointer for timing loops (the caller keeps W alive and unchanged)
         static TcPlaneCache* bench_cache = tc_cache_create();
         gemm_tc(g, (cudaStream_t)stream, mode == 2 ? bench_cache : nullptr);
+    } else if (mode == 7) {
+        gemm_simt_splitk(g, (cudaStream_t)stream);
     } else {
         gemm_simt(g, (cudaStream_t)stream);
     }

@@ -65,3 +65,21 @@ def test_cta_pair_gemm_is_bit_identical_to_single_cta(m, n, k, built_lib):
     w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
     b = torch.randn(n, device="cuda", generator=g)
     assert torch.equal(engine.gemm(a, w, b, mode=3), engine.gemm(a, w, b, mode=5))
+
+
+@pytest.mark.parametrize("m,n,k", [(368, 640, 768), (380, 512, 1024), (100, 128, 64), (777, 64, 128), (40, 384, 384),
+                                   (3000, 128, 1536), (65, 1536, 128), (1, 128, 128)])
+def test_simt_splitk_cluster_gemm(m, n, k, built_lib):
+    """Latency variant for small molecules: 64 x 64 tiles, K split over a thread-block cluster, partial tiles summed
+    through distributed shared memory in rank order.  fp32-exact-grade, and a row's bits never depend on M."""
+    from pdb2reaction_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(m + 2 * n + k)
+    a = torch.randn(m, k, device="cuda", generator=g)
+    w = torch.randn(n, k, device="cuda", generator=g) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=g)
+    c = engine.gemm(a, w, b, mode=7)
+    ref = (a.double() @ w.double().T + b.double())
+    assert (c.double() - ref).abs().max() < 2e-5 * ref.abs().max()
+    assert torch.equal(engine.gemm(a, w, b, mode=7), c)                          # run-to-run
+    big = torch.cat([torch.randn(131, k, device="cuda", generator=g), a, torch.randn(7, k, device="cuda", generator=g)])
+    assert torch.equal(engine.gemm(big, w, b, mode=7)[131:131 + m], c)           # batch / tile position independent

@@ -99,7 +99,9 @@ def test_fd_hessian_columns_on_the_tensor_core_path(built_lib, small_model, hess
     calc._fd_columns_into(hmat, coords, cols)
     h = hmat[:, cols].T.cpu().numpy()
     ref = g["hessian_columns"]
-    # fp32 forces (~2e-6 eV/A noise) differenced over 2e-3 A: ~2e-3 eV/A^2 absolute noise; truncation O(h^2) is smaller
-    assert np.abs(h - ref).max() < 5e-3 * max(1.0, np.abs(ref).max() / 10), np.abs(h - ref).max()
+    # central differences with the reference's fixed step h = 1e-3 A amplify the force error by 1/h: the bf16x3 forces
+    # carry ~2e-5 eV/A (tolerance 1e-4) -> ~1e-2 eV/A^2 noise on entries of up to 2.2 eV/A^2 (measured 9.5e-3); the
+    # analytic columns above have no such amplification (2e-4 relative)
+    assert np.abs(h - ref).max() < 2.5e-2, np.abs(h - ref).max()
     untouched = [k for k in range(480) if k not in cols]
     assert float(hmat[:, untouched].abs().max()) == 0.0

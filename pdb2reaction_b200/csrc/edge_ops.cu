@@ -262,39 +262,6 @@ gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __re
     }
 }
 
-// Variant with all 18 node rows and the whole Wigner record in flight (more memory-level parallelism per warp,
-// 128 registers -> 2 CTAs per SM).  Selected at run time (UMAB_GRS_VARIANT=1) for A/B measurements.
-template <class S>
-__global__ void __launch_bounds__(256, min_blocks<S>(2))
-gather_rotate_scale_wide_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
-                                long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
-    using V = typename VecOf<S>::type;
-    const int el = blockIdx.x * 8 + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (el >= n_e) return;
-    const long long e = e0 + el;
-    const WigReg<S> w = load_wig<S>(wig, e);
-    const long long rp = (long long)el * RAD1 + lane * 4;
-    const long long i0 = (long long)el * 768 + lane * 4, i1 = (long long)el * 1024 + lane * 4,
-                    i2 = (long long)el * 512 + lane * 4;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int node = half == 0 ? src[e] : tgt[e];
-        const long long xp = (long long)node * (9 * C) + lane * 4;
-        V xr[9], yl[9];
-#pragma unroll
-        for (int r = 0; r < 9; ++r) xr[r] = x.ldg4(xp + r * C);
-        rot_fwd(w, xr, yl);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const V o = vmul(yl[to_m(k)], rad.ldg4(rp + r_off(k) + half * C));
-            if (a_buf(k) == 0) A0.st4(i0 + a_off(k) + half * C, o);
-            else if (a_buf(k) == 1) A1.st4(i1 + a_off(k) + half * C, o);
-            else A2.st4(i2 + a_off(k) + half * C, o);
-        }
-    }
-}
-
 // adjoint: one warp per TARGET node of the chunk, looping over its CSR row.
 //   g_rad [E,1536] (A operand of the radial adjoint GEMM; never aliases rad);  G[e] = dL/dx[src] contribution [9,128] (l-primary);
 //   g_x[i] = sum over the row of the target-half contributions;  g_wig[e] += ...
@@ -696,9 +663,7 @@ template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
                                   AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st) {
     if (n_e <= 0) return;
-    static const bool wide = [] { const char* e = getenv("UMAB_GRS_VARIANT"); return e && atoi(e) == 1; }();
-    if (wide) gather_rotate_scale_wide_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
-    else gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>

@@ -1297,12 +1297,11 @@ int32_t umab_gemm(int32_t mode, const float* a_dev, const float* w_dev, const fl
     GemmArgs g;
     g.A = a_dev; g.lda = k; g.W = w_dev; g.ldw = k; g.Cmat = c_dev; g.ldc = n; g.bias = bias_dev;
     g.M = (int)m; g.N = n; g.K = k;
-    if (mode >= 3 && mode <= 6) {
-        // TMA-fed kernel (gemm_tc2.cu): single-CTA with k block 64 / 32 (modes 3 / 4), CTA pair with k block 64 / 32
-        // (modes 5 / 6); the fp32 activation is split into planes for the call
-        const int bk = (mode == 3 || mode == 5) ? 64 : 32;
-        if (!gemm_tc2_supported(g, bk)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
-        gemm_tc2(g, (cudaStream_t)stream, nullptr, bk, mode >= 5 ? 1 : 0);
+    if (mode == 3 || mode == 5) {
+        // TMA-fed kernel (gemm_tc2.cu): single-CTA (mode 3) / CTA pair (mode 5, the engine's default); the fp32
+        // activation is split into planes for the call
+        if (!gemm_tc2_supported(g, 64)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
+        gemm_tc2(g, (cudaStream_t)stream, nullptr, 64, mode == 5 ? 1 : 0);
     } else if (mode == 1 || mode == 2) {
         if (!gemm_tc_supported(g)) throw CudaError("shape not supported by the tensor-core GEMM");
         // mode 1: weight planes rebuilt on every call (never cached by pointer);
@@ -1327,8 +1326,8 @@ int32_t umab_gemm_bench(int32_t mode, const float* a_dev, const float* w_dev, fl
     static TcPlaneCache* c1 = tc_cache_create();
     static Tc2Cache* c2 = tc2_cache_create();
     __nv_bfloat16 *hi = nullptr, *lo = nullptr;
-    const int bk = (mode == 4 || mode == 6) ? 32 : 64;
-    const bool tc2 = mode >= 3 && mode <= 6;
+    const int bk = 64;
+    const bool tc2 = mode == 3 || mode == 5;
     if (tc2) {
         if (!gemm_tc2_supported(g, bk)) throw CudaError("shape not supported by the TMA-fed tensor-core GEMM");
         UMAB_CUDA(cudaMalloc(&hi, (size_t)m * k * 2));

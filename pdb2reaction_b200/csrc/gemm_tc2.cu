@@ -14,7 +14,7 @@
 //               warps of a quadrant) -> (+bias) -> 128B-swizzled staging tile in smem -> TMA tensor store
 //               (cp.async.bulk.tensor global <- shared; rows beyond M are clipped by the tensor map).  It overlaps
 //               the next tile's main loop through the double-buffered TMEM accumulator.
-// BK = 64 bf16 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, twice the stages for the same shared memory).
+// BK = 64 bf16 (SWIZZLE_128B rows).
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -553,20 +553,9 @@ void launch_tc2_pair(const CUtensorMap& ah, const CUtensorMap& al, const Planes2
 
 }  // namespace
 
-// k-block width per shape.  64 (128 B TMA rows) is the faster layout whenever the 256-wide N tile is used; the
-// 32-wide block (twice the pipeline stages) wins where the stage count is the limiter: the 160-wide tiles of
-// N = 640 with its long K loop, and the 128 x 128 radial layer (measured: profiles/r01_gemm_tc2_shapes.txt).
-int tc2_pick_bk(int N, int K) {
-    static const int forced = [] {
-        const char* e = getenv("UMAB_TC2_BK");
-        const int v = e ? atoi(e) : 0;
-        return (v == 32 || v == 64) ? v : 0;
-    }();
-    if (forced) return forced;
-    if ((N == 640 && K == 768) || (N == 128 && K == 128)) return 32;
-    return 64;
-}
-
+// k-block width: 64 bf16 (128 B TMA rows, SWIZZLE_128B).  A 32-wide block (twice the stages) was measured in round 1
+// (profiles/r01_gemm_pair_shapes.txt, r01_gemm_tc2_shapes.txt): never faster on the CTA-pair kernel, +1 % on two shapes
+// of the single-CTA kernel that the pair kernel beats by 15 %; its instantiations were removed in round 2.
 // CTA-pair kernel by default (UMAB_TC2_PAIR=0 selects the single-CTA kernel)
 bool tc2_pair_default() {
     static const bool on = [] {
@@ -582,8 +571,8 @@ void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int p
     // default: the CTA-pair kernel with 64-wide k blocks; the two shapes it does not win (measured,
     // profiles/r01_gemm_pair_shapes.txt) stay on the single-CTA kernel
     if (pair < 0) pair = (tc2_pair_default() && !((a.N == 128 && a.K == 64) || (a.N == 384 && a.K == 128))) ? 1 : 0;
-    if (bk == 0) bk = pair ? 64 : tc2_pick_bk(a.N, a.K);
-    if (bk != 64 && bk != 32) throw CudaError("gemm_tc2: bk must be 64 or 32");
+    if (bk == 0) bk = 64;
+    if (bk != 64) throw CudaError("gemm_tc2: the k block is 64");
     if (!gemm_tc2_supported(a, bk)) throw CudaError("gemm_tc2: unsupported shape");
     int dev = 0;
     UMAB_CUDA(cudaGetDevice(&dev));
@@ -632,10 +621,8 @@ void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int p
     dim3 grid((unsigned)std::min<long long>(tiles, n_sm[dev & 15]));
     if (pair) {
         const long long pair_tiles = (long long)(a.N / pl.bn) * ((a.M + 2 * BM - 1) / (2 * BM));
-        if (bk == 64) launch_tc2_pair<64>(ah, al, pl, cm, p, smem, pair_tiles, st);
-        else launch_tc2_pair<32>(ah, al, pl, cm, p, smem, pair_tiles, st);
-    } else if (bk == 64) launch_tc2<64>(ah, al, pl, cm, p, smem, grid, st);
-    else launch_tc2<32>(ah, al, pl, cm, p, smem, grid, st);
+        launch_tc2_pair<64>(ah, al, pl, cm, p, smem, pair_tiles, st);
+    } else launch_tc2<64>(ah, al, pl, cm, p, smem, grid, st);
     if (!cache || tmp_hi) {
         UMAB_CUDA(cudaStreamSynchronize(st));
         if (!cache) { cudaFree(pl.hi); cudaFree(pl.lo); }

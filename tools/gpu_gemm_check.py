@@ -16,8 +16,8 @@ def main():
         b = torch.randn(n, device="cuda")
         ref = a.double() @ w.double().T + b.double()
         out = {}
-        for mode, name in ((0, "simt"), (1, "tc"), (3, "tc2/64"), (4, "tc2/32")):
-            if mode >= 3 and (k % 64 or n % 32):
+        for mode, name in ((0, "simt"), (1, "tc"), (3, "tc2/64"), (5, "pair/64"), (7, "simt split-K")):
+            if mode in (3, 5) and (k % 64 or n % 32):
                 out[name] = float("nan")
                 continue
             c = engine.gemm(a, w, b, mode=mode)
@@ -35,8 +35,8 @@ def main():
     for (m, n, k) in shapes:
         a = torch.randn(m, k, device="cuda"); w = torch.randn(n, k, device="cuda") / k ** 0.5
         line = f"M={m} N={n} K={k}:"
-        for mode, name in ((2, "tc"), (3, "tc2/64"), (4, "tc2/32")):
-            if mode >= 3 and (k % 64 or n % 32):
+        for mode, name in ((2, "tc"), (3, "tc2/64"), (5, "pair/64")):
+            if mode in (3, 5) and (k % 64 or n % 32):
                 continue
             ms = engine.gemm_bench(a, w, mode, iters=5)
             line += f"  {name} {ms:.3f} ms {2.0 * m * n * k / ms / 1e9:6.1f} TF/s"

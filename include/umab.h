@@ -166,6 +166,11 @@ UMAB_API int64_t umab_hessian_mw_workspace(int32_t n, int32_t r);
 UMAB_API int32_t umab_hessian_mw_project(double* hessian_dev, int32_t n, const double* inv_sqrt_m_dev, const double* q_dev,
                                          int32_t r, double* workspace_dev, int64_t workspace_doubles, void* stream);
 
+/* Free the engine's per-call device memory (edge workspace, per-layer stores, per-edge / per-node state, captured
+ * graphs); weights stay, everything re-grows on the next call.  For hosts that keep several engines (compositions)
+ * alive on one GPU: the reference re-creates calculators per composition, uma_pysis.py:502-504. */
+UMAB_API int32_t umab_release_workspace(umab_engine* e);
+
 /* Counters since creation: kernel launches issued by this library and bytes allocated. */
 UMAB_API int32_t umab_stats(umab_engine* e, int64_t* kernel_launches, int64_t* device_bytes);
 

@@ -85,6 +85,14 @@ def _engine_cache_get(key):
 
 def _engine_cache_put(key, eng, n_devices: int = 1):
     with _state_lock:
+        # a new composition on this GPU: the engines already cached there give their workspace / stores back (tens of
+        # GB each, sized for their own batches); they re-grow if those calculators are used again
+        for k, other in _engine_cache.items():
+            if k[-1] == key[-1] and other is not eng and hasattr(other, "release_workspace"):
+                try:
+                    other.release_workspace()
+                except Exception:
+                    pass
         _engine_cache[key] = eng
         _engine_cache.move_to_end(key)
         per_dev: Dict[int, int] = {}

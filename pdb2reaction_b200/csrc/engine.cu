@@ -916,6 +916,19 @@ struct umab_engine {
             launch_force_reduce(plane(gp<S>(g_vec), k), row_ptr.i(), sptr.i(), sedge.i(), n_nodes, plane(forces, k), st);
     }
 
+    // give the per-call device memory back (edge workspace, per-layer stores, per-edge and per-node state): everything
+    // re-grows on the next call.  Weights, their bf16 planes and the learned edge capacity stay.
+    void release_workspace() {
+        drop_graphs();
+        TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
+                        &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
+        for (TBuf* b : tall) b->release();
+        for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore, &rstore, &u1store, &u2store}) for (auto& b : *v) b.release();
+        DevBuf* all[] = {&src, &tgt, &stmp, &sedge, &node_e, &f_dev, &t_dev, &df_dev, &pos_own};
+        for (DevBuf* b : all) b->release();
+        for (auto& kv : dbg) kv.second.first.release();
+        dbg.clear();
+    }
     void drop_graphs() {
         for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();
@@ -1045,6 +1058,16 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
     } else {
         throw CudaError("unknown option: " + n);
     }
+    UMAB_CATCH
+}
+
+int32_t umab_release_workspace(umab_engine* e) {
+    UMAB_TRY
+    if (!e) throw CudaError("null argument");
+    DeviceGuard guard(e->cfg.device);
+    e->resolve_status();
+    UMAB_CUDA(cudaDeviceSynchronize());
+    e->release_workspace();
     UMAB_CATCH
 }
 

@@ -32,7 +32,7 @@ EXPORTS = (
     "umab_finalize_weights", "umab_set_option", "umab_get_option", "umab_set_system", "umab_build_graph", "umab_graph_counts",
     "umab_graph_copy", "umab_energy_forces", "umab_energy_forces_host", "umab_last_call", "umab_forces_jvp", "umab_gemm", "umab_gemm_bench",
     "umab_debug_tensor", "umab_stats", "umab_profile", "umab_profile_read", "umab_profile_name",
-    "umab_hessian_fd_columns", "umab_hessian_mw_workspace", "umab_hessian_mw_project",
+    "umab_hessian_fd_columns", "umab_hessian_mw_workspace", "umab_hessian_mw_project", "umab_release_workspace",
 )
 
 
@@ -93,6 +93,7 @@ def load_library(path: Optional[str] = None):
     lib.umab_hessian_mw_workspace.argtypes = [i32, i32]
     lib.umab_hessian_mw_workspace.restype = i64
     lib.umab_hessian_mw_project.argtypes = [vp, i32, vp, vp, i32, vp, i64, vp]
+    lib.umab_release_workspace.argtypes = [vp]
     lib.umab_profile_name.argtypes = [i32]
     lib.umab_profile_name.restype = ctypes.c_char_p
     for name in EXPORTS:
@@ -339,6 +340,12 @@ class UmabEngine:
     def set_neighbor_mode(self, mode: str):
         """'auto' (shared-memory cell list from 128 atoms per image), 'brute' or 'cell'; identical edge lists."""
         _check(self.lib, self.lib.umab_set_option(self._h, b"neighbor_mode", self.NEIGHBOR_MODES[mode]))
+
+    def release_workspace(self):
+        """Give the per-call device memory (edge workspace, per-layer stores, node state) back; weights stay and the
+        buffers re-grow on the next call."""
+        if getattr(self, "_h", None):
+            _check(self.lib, self.lib.umab_release_workspace(self._h))
 
     def set_option(self, name: str, value: int):
         """Run-time switches of include/umab.h: "nosync", "cuda_graphs", "neighbor_mode", ..."""

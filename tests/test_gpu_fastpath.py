@@ -89,3 +89,19 @@ def test_batch_composition_never_changes_an_image(built_lib, state4, arch4):
         for eng in (fast, slow):
             e1, f1 = eng.energy_forces_host(pos[2:3])
             assert np.array_equal(e1[0], e[2]) and np.array_equal(f1[0], f[2]), n
+
+
+def test_release_workspace_gives_memory_back_and_results_do_not_change(built_lib, state4, arch4):
+    elem, imgs = synth.make_string(300, 3, 5)
+    fast, slow = _engines(state4, arch4, elem)
+    slow.close()
+    pos = imgs.astype(np.float32)
+    e0, f0 = fast.energy_forces_host(pos)
+    e0, f0 = fast.energy_forces_host(pos)
+    before = fast.stats()["device_bytes"]
+    fast.release_workspace()
+    after = fast.stats()["device_bytes"]
+    assert after < 0.2 * before                       # weights + graph arrays stay, the per-call buffers are gone
+    for _ in range(3):                                # re-grow, capture, replay
+        e1, f1 = fast.energy_forces_host(pos)
+        assert np.array_equal(e0, e1) and np.array_equal(f0, f1)

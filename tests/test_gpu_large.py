@@ -53,6 +53,24 @@ def test_c4_image_values_match_the_float64_oracle(built_lib, state4, arch4):
     assert np.array_equal(e32[k], e[0]) and np.array_equal(f32[k], f[0])
 
 
+def test_whole_c4_string_matches_the_float64_oracle(built_lib, small_model):
+    """North-star target: "reproduces reference energies, forces ... on a 32-image, 1500-atom DMF string".  All 32 images
+    through the PUBLIC calculator call (one get_forces_batch, sub-batched inside the library) against float64-oracle
+    values of every image (fixture: 56 CPU-minutes, tests/golden/make_large_golden.py string)."""
+    path = os.path.join(LARGE, "c4_string_n1500_b32.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    from pdb2reaction_b200 import EV2AU, F_EVAA_2_AU
+    g = np.load(path)
+    elem, imgs = synth.make_config("C4")
+    calc = uma_pysis(model="test-4x")
+    r = calc.get_forces_batch(elem, imgs.reshape(32, -1) * ANG2BOHR)
+    de = np.abs(r["energy"] / EV2AU - g["energy"]) / 1500
+    df = np.abs(r["forces"].reshape(32, 1500, 3) / F_EVAA_2_AU - g["forces"].astype(np.float64)).max(axis=(1, 2))
+    assert de.max() < TOL_E_PER_ATOM and df.max() < TOL_F, (de.max(), df.max())
+    assert calc._core.backend.engines[0].last_call_subcalls >= 1
+
+
 def test_c5_image_values_closed_and_open_chunks(built_lib, state4, arch4):
     g = np.load(os.path.join(LARGE, "c5_n10000.npz"))
     elem, imgs = synth.make_config("C5")

@@ -120,6 +120,13 @@ struct GemmArgs {
     // rounded to bf16 (a_hi w_hi + a_lo w_hi); 3 bf16 x2 with the activations rounded to bf16 (a_hi w_hi + a_hi w_lo);
     // 4 single-pass bf16
     int round_mode = 0;
+    // fused gate epilogue (CTA-pair tensor-core GEMM only; conv-1 m = +-1 / +-2 GEMMs of the forward): besides C the
+    // kernel writes  C[r, n] * gate[r, gcol(n)]  as bf16 hi / lo planes (the A operand of the conv-2 GEMM), where
+    // gate = sigmoid of the gate pre-activations [M, gate_ld] written by gate_b0_kernel and
+    // gcol(n) = ((n >> 7) & 1) * 128 + (n & 127)  (gate_mode 1: m = +-1 rows alternate l = 1, 2)  or
+    //           128 + (n & 127)                    (gate_mode 2: m = +-2 rows, l = 2 only)
+    const float* gate = nullptr; int gate_ld = 0; int gate_mode = 0;
+    __nv_bfloat16* out_hi = nullptr; __nv_bfloat16* out_lo = nullptr;
 };
 
 void gemm_simt(const GemmArgs& a, cudaStream_t st);

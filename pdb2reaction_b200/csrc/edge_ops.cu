@@ -480,6 +480,27 @@ combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B
     B2.st4(b2 + 128, vmul(Y2.ldg4(y2 + 128), g[1]));
 }
 
+// Fused-gate path (float, tensor-core GEMMs): only the m = 0 part of the combine runs as a kernel -- it also leaves
+// sigmoid(gate pre-activations) [n_e, 256] for the conv-1 m = +-1 / +-2 GEMMs, whose epilogues apply the gate and write
+// B1 / B2 themselves (gemm_tc2.cu).  Same arithmetic, same bits as combine_gate_fwd_kernel.
+__global__ void __launch_bounds__(256, 4)
+gate_b0_kernel(GP<float> Y0, int n_e, AP<float> B0, float* __restrict__ sg) {
+    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (el >= n_e) return;
+    const long long y0 = (long long)el * 640 + lane * 4;
+    float4 g[2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        g[l] = vsigmoid(Y0.ldg4(y0 + l * 128));
+        st4(sg + (long long)el * 256 + l * 128 + lane * 4, g[l]);
+    }
+    const long long b0 = (long long)el * 384 + lane * 4;
+    B0.st4(b0, vsilu(Y0.ldg4(y0 + 256)));
+    B0.st4(b0 + 128, vmul(Y0.ldg4(y0 + 384), g[0]));
+    B0.st4(b0 + 256, vmul(Y0.ldg4(y0 + 512), g[1]));
+}
+
 // gY* (A operands of the conv-1 adjoint GEMMs) never alias Y*
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
@@ -701,6 +722,12 @@ void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, 
     combine_gate_fwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
     UMAB_LAUNCH_CHECK();
 }
+void launch_gate_b0(GP<float> Y0, int n_e, AP<float> B0, float* sg, cudaStream_t st) {
+    if (n_e <= 0) return;
+    gate_b0_kernel<<<(n_e + 7) / 8, 256, 0, st>>>(Y0, n_e, B0, sg);
+    UMAB_LAUNCH_CHECK();
+}
+
 template <class S>
 void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
                                AP<S> gY1, AP<S> gY2, cudaStream_t st) {

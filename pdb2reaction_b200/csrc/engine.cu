@@ -38,6 +38,7 @@ void tc2_cache_destroy(Tc2Cache* c);
 void tc2_cache_clear(Tc2Cache* c);
 void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int pair = -1);
 bool gemm_tc2_supported(const GemmArgs& a, int bk);
+bool gemm_tc2_gate_epilogue_available();
 void tc2_split(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 void launch_fd_columns(const float* f, const int* ks, int n_cols, int dof, double h_step, void* hmat, long long ldh,
                        bool f64, cudaStream_t st);                                         // hessian_ops.cu
@@ -250,6 +251,11 @@ struct umab_engine {
     DevBuf node_e;
     // edge workspace
     TBuf wA, wY, wB, wZ, wRAD, wU1, wH1, wU2, wH2, wGY, wGZ;
+    DevBuf wSG;                                        // sigmoid(gates) [chunk, 256] of the fused-gate path
+    // OFF by default: measured (round 2, two boxes) combine_gate_fwd 19.9 -> 9.9 ms but GEMMs +10.6 .. +15.3 ms per C4 step
+    // (net +4 .. +5 ms): the epilogue moves 9.5 KB per edge and layer where the separate kernel moved 10.2 KB, and under
+    // the 1000 W cap a byte costs the same inside the GEMM epilogue.  Bit-identical either way.
+    bool opt_fuse_gate = [] { const char* e = getenv("UMAB_FUSE_GATE"); return e && atoi(e) != 0; }();
     long long chunk_cap = 0;
     // store mode: conv-1 / conv-2 outputs of every layer are kept for the backward instead of being
     // recomputed (16.4 KB per edge and layer of HBM) when they fit `store_bytes`
@@ -407,6 +413,16 @@ struct umab_engine {
             g.M = (int)M; g.N = N; g.K = K; g.accumulate = 0;
             gemm(g, st);
         }
+    }
+    // conv-1 m != 0 GEMM with the gate applied in the epilogue (float, CTA-pair kernel): C = A W^T (fp32, kept) and
+    // C * sigmoid(gate) as the bf16 planes `Bout` of the conv-2 GEMM
+    void mm_gated(AP<float> A, const float* Wt, int N, int K, GP<float> Cm, long long M, int gate_mode, AP<float> Bout,
+                  cudaStream_t st) {
+        GemmArgs g;
+        g.A = A.p; g.A_hi = A.hi; g.A_lo = A.lo; g.lda = K; g.W = Wt; g.ldw = K; g.Cmat = Cm.p; g.ldc = N;
+        g.M = (int)M; g.N = N; g.K = K;
+        g.gate = wSG.f(); g.gate_ld = 256; g.gate_mode = gate_mode; g.out_hi = Bout.hi; g.out_lo = Bout.lo;
+        gemm(g, st);
     }
     // per-coefficient SO(3) linear: rows (n, i) use weight l(i);  A [N,9,K] -> C [N,9,Nout]
     template <class S>
@@ -605,6 +621,7 @@ struct umab_engine {
         wRAD.ensure<S>(f * 1536);
         wU1.ensure<S>(f * 128); wH1.ensure<S>(f * 128); wU2.ensure<S>(f * 128); wH2.ensure<S>(f * 128);
         if (extra) { wGY.ensure<S>(f * std::max(YW, 1536)); wGZ.ensure<S>(f * ZW); }
+        if (std::is_same<S, float>::value) wSG.ensure(f * 256);
     }
 
     // ------------------------------------------------------------------ edge stages
@@ -693,10 +710,24 @@ struct umab_engine {
         timed(P_GATHER, P * (c.n_e * 15512.0 + c.n_nodes * 4608.0), st, [&] {
             launch_gather_rotate_scale_t<S>(n1, src.i(), tgt.i(), gp<S>(wig), b.rad, c.e0, c.n_e, b.a0, b.a1, b.a2, st); });
         mm_ap<S>(b.a0, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, st);
+        if constexpr (std::is_same<S, float>::value) {
+            if (opt_fuse_gate && use_tc() && gemm_tc2_gate_epilogue_available() && c.n_e > 0) {
+                // gate fused into the conv-1 GEMM epilogues: the m = 0 part (needs its own gate columns, other N tiles
+                // of the same GEMM) stays a small kernel that also leaves sigmoid(gates); the m = +-1 / +-2 GEMMs
+                // write Y (kept for the backward) AND the gated bf16 planes B1 / B2 -- Y1 / Y2 are never re-read and
+                // B1 / B2 never pass through a separate kernel (same bits as the un-fused path)
+                timed(P_COMBINE, c.n_e * (640 + 384 + 256) * 4.0, st, [&] {
+                    launch_gate_b0(b.y0, c.n_e, b.b0, wSG.f(), st); });
+                mm_gated(b.a1, w.c1m1, 512, 1024, b.y1, c.n_e, 1, b.b1, st);
+                mm_gated(b.a2, w.c1m2, 256, 512, b.y2, c.n_e, 2, b.b2, st);
+                goto conv2;
+            }
+        }
         mm_ap<S>(b.a1, w.c1m1, 512, 1024, b.y1, 512, c.n_e, nullptr, st);
         mm_ap<S>(b.a2, w.c1m2, 256, 512, b.y2, 256, c.n_e, nullptr, st);
         timed(P_COMBINE, P * c.n_e * (YW + 1152) * 4.0, st, [&] {
             launch_combine_gate_fwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, st); });
+    conv2:
         mm_ap<S>(b.b0, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, st);
         mm_ap<S>(b.b1, w.c2m1, 512, 512, b.z1, 512, c.n_e, nullptr, st);
         mm_ap<S>(b.b2, w.c2m2, 256, 256, b.z2, 256, c.n_e, nullptr, st);
@@ -924,7 +955,7 @@ struct umab_engine {
                         &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
         for (TBuf* b : tall) b->release();
         for (auto* v : {&xs, &x1s, &y1s, &gps, &ystore, &zstore, &rstore, &u1store, &u2store}) for (auto& b : *v) b.release();
-        DevBuf* all[] = {&src, &tgt, &stmp, &sedge, &node_e, &f_dev, &t_dev, &df_dev, &pos_own};
+        DevBuf* all[] = {&src, &tgt, &stmp, &sedge, &node_e, &f_dev, &t_dev, &df_dev, &pos_own, &wSG};
         for (DevBuf* b : all) b->release();
         for (auto& kv : dbg) kv.second.first.release();
         dbg.clear();
@@ -944,7 +975,7 @@ struct umab_engine {
         tc2_cache_destroy(tc2_cache);
         for (auto& kv : weights) kv.second.buf.release();
         DevBuf* all[] = {&z1, &pos_own, &zt, &deg, &thr, &row_ptr, &src, &tgt, &odeg, &sptr, &cursor, &stmp, &sedge,
-                         &cgrid, &ccount, &cstart, &catoms, &acell, &node_e, &e_dev, &f_dev, &t_dev, &df_dev};
+                         &cgrid, &ccount, &cstart, &catoms, &acell, &node_e, &e_dev, &f_dev, &t_dev, &df_dev, &wSG, &status_dev};
         for (DevBuf* b : all) b->release();
         TBuf* tall[] = {&vec, &dist, &env, &wig, &gauss, &g_gauss, &g_env, &g_wig, &g_vec, &nbuf, &abuf, &gx, &gx1,
                         &gn, &ggp, &p1, &s1, &p2, &gp2, &gs1, &Gbuf, &wA, &wY, &wB, &wZ, &wRAD, &wU1, &wH1, &wU2, &wH2, &wGY, &wGZ};
@@ -1048,6 +1079,9 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
         e->neighbor_mode = (int)value;
     } else if (n == "nosync") {
         e->opt_nosync = value != 0;
+    } else if (n == "fuse_gate") {
+        e->opt_fuse_gate = value != 0;
+        e->drop_graphs();
     } else if (n == "cuda_graphs") {
         e->opt_graphs = value != 0;
         if (!e->opt_graphs) e->drop_graphs();
@@ -1077,6 +1111,7 @@ int32_t umab_get_option(umab_engine* e, const char* name, int64_t* value) {
     const std::string n(name);
     if (n == "nosync") *value = e->opt_nosync;
     else if (n == "cuda_graphs") *value = e->opt_graphs;
+    else if (n == "fuse_gate") *value = e->opt_fuse_gate;
     else if (n == "graph_replays") *value = e->graph_replays;
     else if (n == "graph_captures") *value = e->graph_captures;
     else if (n == "overflow_retries") *value = e->overflow_retries;

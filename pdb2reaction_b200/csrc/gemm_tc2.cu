@@ -37,6 +37,9 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct Tc2Params {
     const float* bias;
     int M, N, K, BN, stages, tmem_cols;
+    // fused gate epilogue (pair kernel; see GemmArgs)
+    const float* gate; int gate_ld, gate_mode;
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
 };
 
 template <int BK>
@@ -331,6 +334,21 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
                 }
+                // fused gate: the 32 x 32 tile of this chunk is re-read from the staging tile below with 8 lanes per row, so
+                // that gate loads (128 B per row) and plane stores (64 B per row and plane) are whole sectors; the gate
+                // values are requested here, while the TMEM load is in flight
+                const int col0 = n0 + ch * 32;
+                const int sub_r = lane >> 3, sub_j = lane & 7;
+                float4 gv[8];
+                if (p.gate) {
+                    const int gcol = (p.gate_mode == 1 ? ((col0 >> 7) & 1) * 128 : 128) + (col0 & 127) + sub_j * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int grow = mrow0 + it * 4 + sub_r;
+                        gv[it] = grow < p.M ? __ldg(reinterpret_cast<const float4*>(p.gate + (long long)grow * p.gate_ld + gcol))
+                                            : f4zero();
+                    }
+                }
                 tmem_ld_wait();
                 if (lane == 0) tma_store_wait_read0();
                 __syncwarp();
@@ -347,6 +365,24 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_con
                 if (lane == 0 && mrow0 < p.M) {
                     tma_store_2d(&tm_c, stg, n0 + ch * 32, mrow0);
                     tma_store_commit();
+                }
+                if (p.gate) {
+                    // gated bf16 planes of conv-2: the same fp32 product and hi / lo split as combine_gate_fwd_kernel
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + sub_r;
+                        const int grow = mrow0 + r;
+                        float4 o;
+                        const uint32_t addr = stg + (uint32_t)r * 128u + ((((uint32_t)sub_j) ^ (uint32_t)(r & 7)) << 4);
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(addr));
+                        if (grow < p.M) {
+                            uint2 h, l;
+                            split4(f4mul(o, gv[it]), h, l);
+                            const long long oi = (long long)grow * p.N + col0 + sub_j * 4;
+                            *reinterpret_cast<uint2*>(p.out_hi + oi) = h;
+                            *reinterpret_cast<uint2*>(p.out_lo + oi) = l;
+                        }
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -557,6 +593,9 @@ void launch_tc2_pair(const CUtensorMap& ah, const CUtensorMap& al, const Planes2
 // (profiles/r01_gemm_pair_shapes.txt, r01_gemm_tc2_shapes.txt): never faster on the CTA-pair kernel, +1 % on two shapes
 // of the single-CTA kernel that the pair kernel beats by 15 %; its instantiations were removed in round 2.
 // CTA-pair kernel by default (UMAB_TC2_PAIR=0 selects the single-CTA kernel)
+bool tc2_pair_default();
+// the fused gate epilogue lives in the pair kernel only
+bool gemm_tc2_gate_epilogue_available() { return tc2_pair_default(); }
 bool tc2_pair_default() {
     static const bool on = [] {
         const char* e = getenv("UMAB_TC2_PAIR");
@@ -607,6 +646,9 @@ void gemm_tc2(const GemmArgs& a, cudaStream_t st, Tc2Cache* cache, int bk, int p
     }
     Tc2Params p;
     p.bias = a.bias; p.M = a.M; p.N = a.N; p.K = a.K; p.BN = pl.bn;
+    p.gate = a.gate; p.gate_ld = a.gate_ld; p.gate_mode = a.gate_mode; p.out_hi = a.out_hi; p.out_lo = a.out_lo;
+    if (a.gate && (!pair || !a.out_hi || !a.out_lo || a.N % 128 != 0 || (a.gate_mode != 1 && a.gate_mode != 2)))
+        throw CudaError("gemm_tc2: the fused gate epilogue needs the CTA-pair kernel, output planes and N % 128 == 0");
     const int stage_bytes = 2 * BM * bk * 2 + 2 * (pair ? pl.bn / 2 : pl.bn) * bk * 2;
     const int fixed = EPI_WARPS * STG_BYTES + 1024 /*alignment slack*/ + 8 * (2 * 8 + 5) + 64;
     p.stages = std::max(2, std::min(8, (SMEM_LIMIT - fixed) / stage_bytes));

@@ -58,6 +58,8 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st);
 template <class S>
 void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st);
+// fused-gate path: m = 0 part of the combine + sigmoid(gates) [n_e, 256] for the GEMM epilogues
+void launch_gate_b0(GP<float> Y0, int n_e, AP<float> B0, float* sg, cudaStream_t st);
 template <class S>
 void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
                                AP<S> gY1, AP<S> gY2, cudaStream_t st);

@@ -105,3 +105,29 @@ def test_release_workspace_gives_memory_back_and_results_do_not_change(built_lib
     for _ in range(3):                                # re-grow, capture, replay
         e1, f1 = fast.energy_forces_host(pos)
         assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
+
+
+@pytest.mark.parametrize("n,b", [(130, 2), (300, 3), (1500, 2)])
+def test_fused_gate_epilogue_is_bit_identical_to_the_separate_combine_kernel(n, b, built_lib, state4, arch4):
+    """conv-1 m = +-1 / +-2 GEMMs write the gated bf16 planes of conv-2 from their epilogue (gemm_tc2.cu): the same fp32
+    product and the same split as combine_gate_fwd_kernel -> identical energies and forces, also with chunked /
+    recomputing backward passes and for energy-only calls."""
+    elem, imgs = synth.make_string(n, b, 70 + n)
+    fused, plain = _engines(state4, arch4, elem)
+    for eng in (fused, plain):
+        eng.set_option("nosync", 1)
+        eng.set_option("cuda_graphs", 0)
+    fused.set_option("fuse_gate", 1)                  # off by default (measured: no gain, DESIGN.md 8c)
+    plain.set_option("fuse_gate", 0)
+    assert fused.get_option("fuse_gate") == 1 and plain.get_option("fuse_gate") == 0
+    pos = imgs.astype(np.float32)
+    e0, f0 = plain.energy_forces_host(pos)
+    e1, f1 = fused.energy_forces_host(pos)
+    assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
+    e2, _ = fused.energy_forces_host(pos, forces=False)
+    assert np.array_equal(e2, e0)
+    from pdb2reaction_b200.engine import UmabEngine
+    z, merged = merged_for(state4, arch4, elem)
+    rec = UmabEngine(merged, z, arch4, store_bytes=-1, workspace_bytes=9600 * 4 * 6000)      # recompute + several chunks
+    e3, f3 = rec.energy_forces_host(pos)
+    assert np.array_equal(e0, e3) and np.array_equal(f0, f3)

@@ -1,4 +1,6 @@
 #!/bin/bash
+# round-end checks on one GPU (gpurun): the whole -m gpu suite, smoke(), the N = 1 bench line.  See also gpu_run_scale.sh
+# (1/2/4/8 GPUs + Hessian), gpu_ncu_round.sh (ncu evidence), gpu_latency_sweep.py, gpu_precision_study.py, gpu_overlap_probe.py.
 set -u
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log

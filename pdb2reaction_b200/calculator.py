@@ -204,13 +204,13 @@ class CudaBackend:
         return e_out, f_out
 
     def evaluate_device(self, coords_ang: np.ndarray):
-        """coords [B,N,3] A -> (E [B] fp64 eV, F [B,N,3] fp32 eV/A) as tensors on the FIRST engine's GPU (one pinned
-        H2D of the coordinates, no D2H): the shard evaluation of ``sharding.sharded_get_forces_batch``."""
+        """coords [B,N,3] A -> (E [B] fp64 eV, F [B,N,3] fp32 eV/A) as tensors on the FIRST engine's GPU (one H2D of
+        the coordinates, no D2H): the shard evaluation of ``sharding.sharded_get_forces_batch``."""
         eng = self.engines[0]
         dev = torch.device("cuda", eng.device)
         pos = torch.from_numpy(np.ascontiguousarray(coords_ang, dtype=np.float32))
         with torch.cuda.device(dev):
-            e, f = eng.energy_forces(pos.pin_memory().to(dev, non_blocking=True), True)
+            e, f = eng.energy_forces(pos.to(dev), True)      # 18 KB per image: a pinned staging buffer would cost more
         if not self.transform.is_identity:
             e = e * self.transform.scale + torch.as_tensor(self._e_const, device=dev)
             f = f * float(self.transform.scale)

@@ -156,8 +156,8 @@ def cpu_oracle(args, elem, coords_one, threads=None):
 
 def choose_cpu_sample(args, elem, imgs, n_evals, budget_s):
     """Largest bounded CPU sample that fits ``budget_s`` for ``n_evals`` evaluations: a 300-atom sub-cluster is timed
-    first (it also warms the thread pools up); whole images are used when their projected cost (t ~ n^1.7: edges per atom
-    and cache misses both grow with the cluster) fits, otherwise the largest of 1000 / 600 / 300 atoms that does.
+    first (it also warms the thread pools up); whole images are used when their projected cost (t ~ n^1.3; measured on
+    the box's 16 cores: 1.9 s at 300 atoms, 12.4 s at 1500 = n^1.17) fits, otherwise the largest of 1000 / 600 / 300 that does.
     -> (n_sample, elem_s, imgs_s, oracle, seconds per evaluation of the 300-atom probe)"""
     n0 = min(args.cpu_sample_atoms or 300, args.atoms)
     elem_s, imgs_s = cpu_sample(elem, imgs, n0)
@@ -169,7 +169,7 @@ def choose_cpu_sample(args, elem, imgs, n_evals, budget_s):
     if args.cpu_sample_atoms:
         return n0, elem_s, imgs_s, orc, t_probe
     for n in (args.atoms, 1000, 600):
-        if n0 < n <= args.atoms and n_evals * t_probe * (n / n0) ** 1.7 <= budget_s:
+        if n0 < n <= args.atoms and n_evals * t_probe * (n / n0) ** 1.3 <= budget_s:
             elem_s, imgs_s = cpu_sample(elem, imgs, n)
             return n, elem_s, imgs_s, cpu_oracle(args, elem_s, imgs_s[0], threads=os.cpu_count() or 1), t_probe
     return n0, elem_s, imgs_s, orc, t_probe
@@ -187,8 +187,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     elem, imgs = synth.make_string(args.atoms, args.images, args.seed)
-    # on-config: whole images whenever their (steps + warmup) evaluations fit ~7 minutes (C4: 25 x ~12 s = 5 min)
-    n_s, elem_s, imgs_s, orc, _ = choose_cpu_sample(args, elem, imgs, args.steps + args.warmup, budget_s=420.0)
+    # on-config: whole images whenever their (steps + warmup) evaluations fit ~10 minutes (C4: 25 x ~12.4 s = 5.2 min)
+    n_s, elem_s, imgs_s, orc, _ = choose_cpu_sample(args, elem, imgs, args.steps + args.warmup, budget_s=600.0)
     for w in range(args.warmup):
         orc.energy_forces(imgs_s[w % len(imgs_s)])
     t0 = time.perf_counter()

@@ -104,6 +104,27 @@ __device__ __forceinline__ void vfma(D4& acc, D1 s, D4 b) {
     f4fma(acc.d, s.v, b.d);
     f4fma(acc.d, s.d, b.v);
 }
+// acc += a * b,  acc -= a * b  (elementwise; packed FFMA2)
+__device__ __forceinline__ void f4fmav(float4& acc, float4 a, float4 b) {
+    const float2 lo = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ void vfmav(float4& acc, float4 a, float4 b) { f4fmav(acc, a, b); }
+__device__ __forceinline__ void vfmav(D4& acc, D4 a, D4 b) {
+    f4fmav(acc.v, a.v, b.v);
+    f4fmav(acc.d, a.v, b.d);
+    f4fmav(acc.d, a.d, b.v);
+}
+__device__ __forceinline__ void vfnmav(float4& acc, float4 a, float4 b) {
+    f4fmav(acc, make_float4(-a.x, -a.y, -a.z, -a.w), b);
+}
+__device__ __forceinline__ void vfnmav(D4& acc, D4 a, D4 b) {
+    const float4 na = make_float4(-a.v.x, -a.v.y, -a.v.z, -a.v.w), nd = make_float4(-a.d.x, -a.d.y, -a.d.z, -a.d.w);
+    f4fmav(acc.v, na, b.v);
+    f4fmav(acc.d, na, b.d);
+    f4fmav(acc.d, nd, b.v);
+}
 __device__ __forceinline__ float vdot(float4 a, float4 b) { return f4dot(a, b); }
 __device__ __forceinline__ D1 vdot(D4 a, D4 b) { return {f4dot(a.v, b.v), f4dot(a.v, b.d) + f4dot(a.d, b.v)}; }
 __device__ __forceinline__ float vhsum(float4 a) { return f4hsum(a); }

@@ -96,75 +96,46 @@ __device__ __forceinline__ constexpr int r_off(int k) {
     return k < 3 ? k * 256 : (k == 3 || k == 5 ? 768 : (k == 4 || k == 6 ? 1024 : 1280));
 }
 
-// totals of r[t] over the warp land in lane t (31 shuffles instead of 160)
-template <class S>
-__device__ __forceinline__ S warp_transpose_sum32(S (&r)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool upper = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-            S send = upper ? r[i] : r[i + o];
-            S keep = upper ? r[i + o] : r[i];
-            r[i] = keep + s_shfl_xor(send, o);
-        }
-    }
-    return r[0];
+// ---- gradient with respect to the edge ROTATION as a torque (round 2; replaces the 34 outer-product entries dL/dD).
+// The Wigner blocks depend on the edge direction only through the rotation R_e (D = D(R_e), D1 = R_e), and a change of
+// R_e is an infinitesimal rotation  D -> (1 + sum_k dw_k J_k) D  with the so(3) generators J_k of the l = 1, 2 real
+// harmonic blocks (basis of oracle/wigner.py: l = 1 -> (x, y, z); edge axis = y).  So for y = D x:  dL = sum_k dw_k
+// <g_y, J_k y>, and for the rotate-back  out = s D^T z:  dL = - sum_k dw_k <g_z, J_k z>  with g_z = s D g_out.  The
+// energy is invariant to the rotation about the edge axis (k = y: the roll angle), so only t_x and t_z are kept; the
+// geometry adjoint turns them into dE/d(edge vector) = (t_z R_e[0] - t_x R_e[2]) / d  (geometry.cu).  Two warp
+// reductions per edge and kernel instead of 34, 8 bytes of read-modify-write instead of 288.
+//   J_x:  l=1 (1,2) = -1;  l=2 (0,1) = 1, (2,3) = -sqrt3, (3,4) = -1        (antisymmetric; (a,b) listed, (b,a) = -)
+//   J_z:  l=1 (0,1) = -1;  l=2 (0,3) = -1, (1,2) = -sqrt3, (1,4) = -1
+template <class V> struct TorqueAcc { V x1, xs, z1, zs; };      // unit-weight and sqrt3-weight terms of t_x, t_z
+template <class V>
+__device__ __forceinline__ TorqueAcc<V> torque_zero() { return {vzero<V>(), vzero<V>(), vzero<V>(), vzero<V>()}; }
+// acc += (this lane's 4 channels of)  g^T J_k v ;  g, v: 9 l-primary rows
+template <class V>
+__device__ __forceinline__ void torque_acc(TorqueAcc<V>& t, const V* g, const V* v) {
+    const V* g1 = g + 1; const V* v1 = v + 1; const V* g2 = g + 4; const V* v2 = v + 4;
+    // t_x
+    vfmav(t.x1, g1[2], v1[1]); vfnmav(t.x1, g1[1], v1[2]);
+    vfmav(t.x1, g2[0], v2[1]); vfnmav(t.x1, g2[1], v2[0]);
+    vfmav(t.x1, g2[4], v2[3]); vfnmav(t.x1, g2[3], v2[4]);
+    vfmav(t.xs, g2[3], v2[2]); vfnmav(t.xs, g2[2], v2[3]);
+    // t_z
+    vfmav(t.z1, g1[1], v1[0]); vfnmav(t.z1, g1[0], v1[1]);
+    vfmav(t.z1, g2[3], v2[0]); vfnmav(t.z1, g2[0], v2[3]);
+    vfmav(t.z1, g2[4], v2[1]); vfnmav(t.z1, g2[1], v2[4]);
+    vfmav(t.zs, g2[2], v2[1]); vfnmav(t.zs, g2[1], v2[2]);
 }
-
-// partial (this lane's 4 channels) outer products  acc[(b,a)] += sum_c zl[b][c] g[a][c]  restricted to
-// the l=1 and l=2 blocks; slot order = Wigner record order (D1 row-major, then D2 row-major)
+// old values of the per-edge torque record [E, 4] = (t_x, t_z, 0, 0), requested at the top of the edge's work
+template <class S>
+__device__ __forceinline__ S torque_load(GP<S> g_tau, long long e, int lane) {
+    return lane < 2 ? g_tau.ld(e * 4 + lane) : cst<S>(0.f);
+}
+// warp-reduce and add `scale` times the torque into g_tau[e]
 template <class S, class V>
-__device__ __forceinline__ void wig_outer_acc(S (&acc)[34], const V* zl, const V* g) {
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) acc[b * 3 + a] = acc[b * 3 + a] + vdot(zl[1 + b], g[1 + a]);
-#pragma unroll
-    for (int b = 0; b < 5; ++b)
-#pragma unroll
-        for (int a = 0; a < 5; ++a) acc[9 + b * 5 + a] = acc[9 + b * 5 + a] + vdot(zl[4 + b], g[4 + a]);
-}
-
-// warp-reduce the 34 partials and add them (times `scale`) into g_wig[e]
-template <class S>
-__device__ __forceinline__ void wig_grad_commit(S (&acc)[34], S scale, GP<S> g_wig, long long e, int lane) {
-    S r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = acc[i];
-    S tot = warp_transpose_sum32(r, lane);
-    S t32 = warp_sum(acc[32]);
-    S t33 = warp_sum(acc[33]);
-    const long long o = e * WIG;
-    g_wig.st(o + lane, g_wig.ld(o + lane) + scale * tot);
-    if (lane == 0) g_wig.st(o + 32, g_wig.ld(o + 32) + scale * t32);
-    if (lane == 1) g_wig.st(o + 33, g_wig.ld(o + 33) + scale * t33);
-}
-
-// same with the old g_wig values already in registers (loaded at the top of the iteration: the DRAM round trip of the
-// read-modify-write overlaps the rest of the edge's work instead of stalling its end)
-template <class S> struct WigOld { S a, b; };
-template <class S>
-__device__ __forceinline__ WigOld<S> wig_grad_load(GP<S> g_wig, long long e, int lane) {
-    const long long o = e * WIG;
-    WigOld<S> r;
-    r.a = g_wig.ld(o + lane);
-    r.b = lane < 2 ? g_wig.ld(o + 32 + lane) : cst<S>(0.f);
-    return r;
-}
-template <class S>
-__device__ __forceinline__ void wig_grad_commit_pre(S (&acc)[34], S scale, const WigOld<S>& old, GP<S> g_wig, long long e,
-                                                    int lane) {
-    S r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = acc[i];
-    S tot = warp_transpose_sum32(r, lane);
-    S t32 = warp_sum(acc[32]);
-    S t33 = warp_sum(acc[33]);
-    const long long o = e * WIG;
-    g_wig.st(o + lane, old.a + scale * tot);
-    if (lane == 0) g_wig.st(o + 32, old.b + scale * t32);
-    if (lane == 1) g_wig.st(o + 33, old.b + scale * t33);
+__device__ __forceinline__ void torque_commit(const TorqueAcc<V>& t, S scale, S old, GP<S> g_tau, long long e, int lane) {
+    constexpr float SQ3 = 1.7320508075688772f;
+    const S tx = warp_sum(vhsum(t.x1) + SQ3 * vhsum(t.xs));
+    const S tz = warp_sum(vhsum(t.z1) + SQ3 * vhsum(t.zs));
+    if (lane < 2) g_tau.st(e * 4 + lane, old + scale * (lane == 0 ? tx : tz));
 }
 
 // scalars [LO, LO+N) of the Wigner record of edge e (D1 = 0..8, D2 = 9..33)
@@ -307,9 +278,8 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int half = 1 - hh;
-            S wacc[34];
-#pragma unroll
-            for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
+            TorqueAcc<V> tq = torque_zero<V>();
+            const S tau_old = torque_load<S>(g_wig, e, lane);
             const long long xp = half == 0 ? (long long)src[e] * (9 * C) + lane * 4 : xi_p;
             V xr[9], yl[9], gml[9];
             V g_rad_v[6];      // radial groups 0,1,2 (m=0 rows), 3,4 (m=1: l=1,2), 5 (m=2)
@@ -331,8 +301,7 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
             g_rad.st4(rp + 768 + half * C, g_rad_v[3]);
             g_rad.st4(rp + 1024 + half * C, g_rad_v[4]);
             g_rad.st4(rp + 1280 + half * C, g_rad_v[5]);
-            // dL/dD[a][b] += sum_c gml[a][c] x[b][c]
-            wig_outer_acc(wacc, gml, xr);
+            torque_acc(tq, gml, yl);                 // <g_y, J_k y>,  y = D x
             V gx[9];
             rot_bwd(w, gml, gx);
             if (half == 0) {
@@ -343,7 +312,7 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 #pragma unroll
                 for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
             }
-            wig_grad_commit(wacc, cst<S>(1.0f), g_wig, e, lane);
+            torque_commit(tq, cst<S>(1.0f), tau_old, g_wig, e, lane);
         }
     }
 #pragma unroll
@@ -380,7 +349,7 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
             const long long e_n = HALF == 1 ? (long long)k + 1 : (long long)elist[k + 1];
             const long long en = e_n - e0;
             if (lane < 9) wig.prefetch(e_n * WIG + lane * 4);
-            else if (lane < 18) g_wig.prefetch(e_n * WIG + (lane - 9) * 4);
+            else if (lane == 9) g_wig.prefetch(e_n * 4);
 #pragma unroll
             for (int q = 0; q < RAD1 / 256; ++q) rad.prefetch(en * RAD1 + q * 256 + HALF * C + lane * 4);
 #pragma unroll
@@ -390,13 +359,11 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
 #pragma unroll
             for (int q = 0; q < 2; ++q) gA2.prefetch(en * 512 + q * 256 + HALF * C + lane * 4);
         }
-        const WigOld<S> gw_old = wig_grad_load<S>(g_wig, e, lane);
+        const S tau_old = torque_load<S>(g_wig, e, lane);
         const WigReg<S> w = load_wig<S>(wig, e);
         const long long rp = el * RAD1 + lane * 4;
         const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
-        S wacc[34];
-#pragma unroll
-        for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
+        TorqueAcc<V> tq = torque_zero<V>();
         V yl[9], gml[9];
         V g_rad_v[6];
         rot_fwd(w, xr, yl);
@@ -415,12 +382,12 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
         g_rad.st4(rp + 768 + HALF * C, g_rad_v[3]);
         g_rad.st4(rp + 1024 + HALF * C, g_rad_v[4]);
         g_rad.st4(rp + 1280 + HALF * C, g_rad_v[5]);
-        wig_outer_acc(wacc, gml, xr);
+        torque_acc(tq, gml, yl);                     // <g_y, J_k y>,  y = D x
         V gx[9];
         rot_bwd(w, gml, gx);
 #pragma unroll
         for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
-        wig_grad_commit_pre(wacc, cst<S>(1.0f), gw_old, g_wig, e, lane);
+        torque_commit(tq, cst<S>(1.0f), tau_old, g_wig, e, lane);
     }
     if (HALF == 1) {
 #pragma unroll
@@ -637,7 +604,7 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
     if (el >= n_e) return;
     const long long e = e0 + el;
     // the read-modify-write operands first: their DRAM round trips overlap everything below
-    const WigOld<S> gw_old = wig_grad_load<S>(g_wig, e, lane);
+    const S tau_old = torque_load<S>(g_wig, e, lane);
     S genv_old = cst<S>(0.f);
     if (lane == 0) genv_old = g_env.ld(e);
     const WigReg<S> w = load_wig<S>(wig, e);
@@ -647,21 +614,14 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
 #pragma unroll
     for (int r = 0; r < 9; ++r) g[r] = g_out.ldg4(gp + r * C);
     const S s = env.ldg(e) * scale;
-    // d/denv
-    rot_bwd(w, zl, t);
+    // t = D g serves all three outputs:  d/dz = s t (m-primary rows),  d/denv = scale <D^T z, g> = scale <z, t>,
+    // torque = - s <t, J_k z>
+    rot_fwd(w, g, t);
     S part = cst<S>(0.f);
 #pragma unroll
-    for (int r = 0; r < 9; ++r) part = part + vdot(t[r], g[r]);
+    for (int r = 0; r < 9; ++r) part = part + vdot(t[r], zl[r]);
     part = warp_sum(part);
     if (lane == 0) g_env.st(e, genv_old + part * scale);
-    // d/dD[b][a] = s * sum_c zl[b][c] g[a][c]
-    S wacc[34];
-#pragma unroll
-    for (int q = 0; q < 34; ++q) wacc[q] = cst<S>(0.f);
-    wig_outer_acc(wacc, zl, g);
-    wig_grad_commit_pre(wacc, s, gw_old, g_wig, e, lane);
-    // d/dz (m-primary rows) = s * (D g)[to_m(k)]
-    rot_fwd(w, g, t);
     const long long o0 = (long long)el * 384 + lane * 4;
 #pragma unroll
     for (int k = 0; k < 3; ++k) gZ0.st4(o0 + k * 128, vscale(t[to_m(k)], s));
@@ -676,6 +636,10 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
         gZ2.st4(o2, vscale(t[to_m(7)], s));
         gZ2.st4(o2 + 128, vscale(t[to_m(8)], s));
     }
+    // torque of the rotate-back: - s <D g, J_k z>  (after the stores: they do not wait for the reductions)
+    TorqueAcc<V> tq = torque_zero<V>();
+    torque_acc(tq, t, zl);
+    torque_commit(tq, cst<S>(0.f) - s, tau_old, g_wig, e, lane);
 }
 
 }  // namespace

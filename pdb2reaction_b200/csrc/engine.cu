@@ -244,7 +244,7 @@ struct umab_engine {
         return on;
     }
     // geometry
-    TBuf vec, dist, env, wig, gauss, g_gauss, g_env, g_wig, g_vec;
+    TBuf vec, dist, env, wig, gauss, g_gauss, g_env, g_wig, g_vec;      // g_wig: per-edge torque (t_x, t_z, 0, 0) of the edge frame
     // nodes
     std::vector<TBuf> xs, x1s, y1s, gps;
     TBuf nbuf, abuf, gx, gx1, gn, ggp, p1, s1, p2, gp2, gs1, Gbuf;
@@ -899,10 +899,10 @@ struct umab_engine {
         gx.ensure<S>(nf); gx1.ensure<S>(nf); gn.ensure<S>(nf); ggp.ensure<S>((size_t)n_nodes * 2 * H * 4);
         gs1.ensure<S>((size_t)n_nodes * H * 4);
         if (!chunks_closed) Gbuf.ensure<S>(ne * 9 * C * 4);
-        g_gauss.ensure<S>(ne * NB * 4); g_env.ensure<S>(ne * 4); g_wig.ensure<S>(ne * WIG * 4); g_vec.ensure<S>(ne * 12);
+        g_gauss.ensure<S>(ne * NB * 4); g_env.ensure<S>(ne * 4); g_wig.ensure<S>(ne * 4 * 4); g_vec.ensure<S>(ne * 12);   // g_wig: torque record [E, 4]
         zero<S>(g_gauss, ne * NB * 4, st);
         zero<S>(g_env, ne * 4, st);
-        zero<S>(g_wig, ne * WIG * 4, st);
+        zero<S>(g_wig, ne * 4 * 4, st);
 
         mm<S>(gp<S>(gp2), H, h2_t, H, H, gp<S>(gs1), H, n_nodes, nullptr, 0, st);
         launch_eltwise_t<S>(1, gp<S>(gs1), gp<S>(p1), (long long)n_nodes * H, gp<S>(gs1), st);      // g_p1
@@ -939,7 +939,7 @@ struct umab_engine {
         }
         save_dbg("g_gauss", g_gauss.v.p, (size_t)n_edges * NB, st);
         save_dbg("g_env", g_env.v.p, (size_t)n_edges, st);
-        save_dbg("g_wig", g_wig.v.p, (size_t)n_edges * WIG, st);
+        save_dbg("g_tau", g_wig.v.p, (size_t)n_edges * 4, st);
         launch_geometry_bwd_t<S>(gp<S>(vec), gp<S>(dist), gp<S>(wig), gp<S>(gauss), gp<S>(g_gauss), gp<S>(g_env),
                                  gp<S>(g_wig), (int)n_edges, cfg.cutoff, gp<S>(g_vec), st);
         save_dbg("g_vec", g_vec.v.p, (size_t)n_edges * 3, st);

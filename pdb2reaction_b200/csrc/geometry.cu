@@ -1,6 +1,6 @@
 // K2/K3: per-edge geometry -- edge vector, distance, polynomial envelope, Gaussian distance
 // basis and the closed-form l<=2 Wigner blocks -- and the adjoint that turns the accumulated
-// per-edge gradients (d/dgauss, d/denv, d/dwigner) into dE/d(edge vector).
+// per-edge gradients (d/dgauss, d/denv, and the torque of the edge frame) into dE/d(edge vector).
 //
 // Replaces fairchem's GaussianSmearing / PolynomialEnvelope / init_edge_rot_euler_angles +
 // eulers_to_wigner, reached from the reference through predict_unit.predict
@@ -191,40 +191,21 @@ geometry_bwd_kernel(GP<S> vec, GP<S> dist, GP<S> wig, GP<S> gauss, GP<S> g_gauss
     S denv = (val(u) < 1.0f) ? (u4 * (-105.0f + u * (210.0f - 105.0f * u))) / cutoff : cst<S>(0.f);
     g_d = g_d + g_env.ld(e) * denv;
 
-    S vx = vec.ld(e * 3 + 0), vy = vec.ld(e * 3 + 1), vz = vec.ld(e * 3 + 2);
-    S inv = 1.0f / d;
-    EdgeFrame<S> f = make_frame<S>(vx * inv, vy * inv, vz * inv);
-    M3<S> r, g_rot;
+    // rotation part: the edge kernels accumulated the torque (t_x, t_z) of the edge frame (edge_ops.cu: D -> (1 + dw.J) D);
+    // keeping R_e n = y_hat under a change dn of the direction needs  R_e dn = y_hat x dw = (dw_z, 0, -dw_x), and the
+    // energy does not depend on dw_y (roll angle), so  dL = t_z (R_e dn)_x - t_x (R_e dn)_z  and
+    // dL/dn = t_z R_e[0] - t_x R_e[2]  -- already perpendicular to n = R_e[1]; no pole: any orthonormal frame works
+    const S inv = 1.0f / d;
     const long long wo = (long long)e * WIG;
+    const S tx = g_wig.ld((long long)e * 4 + 0), tz = g_wig.ld((long long)e * 4 + 1);
+    S gn[3], n[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) { r.v[a][b] = wig.ld(wo + a * 3 + b); g_rot.v[a][b] = g_wig.ld(wo + a * 3 + b); }
-    // dL/dR += (4/3) sum_m Q_m R (sum_n G2[m][n] Q_n)
-#pragma unroll
-    for (int m = 0; m < 5; ++m) {
-        S g5[5];
-#pragma unroll
-        for (int n = 0; n < 5; ++n) g5[n] = g_wig.ld(wo + 9 + m * 5 + n);
-        M3<S> t = qleft(m, matmul(r, qcomb(g5)));
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) g_rot.v[a][b] = g_rot.v[a][b] + (4.0f / 3.0f) * t.v[a][b];
+    for (int b = 0; b < 3; ++b) {
+        gn[b] = tz * wig.ld(wo + 0 * 3 + b) - tx * wig.ld(wo + 2 * 3 + b);
+        n[b] = vec.ld(e * 3 + b) * inv;
     }
-    S g_ca = g_rot.v[0][0] + f.y * g_rot.v[2][2];
-    S g_sa = -g_rot.v[0][2] + f.y * g_rot.v[2][0];
-    S g_s = -g_rot.v[2][1];
-    S gx = g_rot.v[1][0];
-    S gy = g_rot.v[1][1] + f.sa * g_rot.v[2][0] + f.ca * g_rot.v[2][2];
-    S gz = g_rot.v[1][2];
-    S g_s_tot = g_s - (g_ca * f.ca + g_sa * f.sa) * f.inv_s;
-    gx = gx + g_sa * f.inv_s + g_s_tot * f.sa;
-    gz = gz + g_ca * f.inv_s + g_s_tot * f.ca;
-    S dotn = gx * f.x + gy * f.y + gz * f.z;
-    g_vec.st(e * 3 + 0, (gx - f.x * dotn) * inv + g_d * f.x);
-    g_vec.st(e * 3 + 1, (gy - f.y * dotn) * inv + g_d * f.y);
-    g_vec.st(e * 3 + 2, (gz - f.z * dotn) * inv + g_d * f.z);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) g_vec.st(e * 3 + b, gn[b] * inv + g_d * n[b]);
 }
 
 // F[i] = sum_{e into i} g_vec[e] - sum_{e out of i} g_vec[e]   (vec = pos[src] - pos[tgt]); linear:

@@ -311,7 +311,6 @@ def main():
         return run_hessian(args, world, rank, local)
 
     from pdb2reaction_b200 import calculator as calc_mod
-    from pdb2reaction_b200 import engine as engine_mod
     from pdb2reaction_b200 import synth, uma_pysis
     from pdb2reaction_b200.arch import UMAArch
     from pdb2reaction_b200.shims import ANG2BOHR

@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from .calculator import uma_pysis, EV2AU, F_EVAA_2_AU
-from .shims import ANG2BOHR, BOHR2ANG
+from .shims import ANG2BOHR
 
 
 # ------------------------------------------------------------------ pysisyphus chain of states

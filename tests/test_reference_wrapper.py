@@ -16,7 +16,6 @@ import pytest
 import torch
 
 import refstubs
-from conftest import merged_for
 from pdb2reaction_b200 import calculator as repo_mod
 from pdb2reaction_b200 import uma_pysis as repo_uma_pysis
 from pdb2reaction_b200 import weights as W

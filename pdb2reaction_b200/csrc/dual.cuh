@@ -104,6 +104,15 @@ __device__ __forceinline__ void vfma(D4& acc, D1 s, D4 b) {
     f4fma(acc.d, s.v, b.d);
     f4fma(acc.d, s.d, b.v);
 }
+// Product that must ROUND AS A PRODUCT even when the next operation adds it to something: ptxas contracts a packed
+// mul.rn.f32x2 with a following add.rn.f32x2 into FFMA2 (the .rn of the packed forms does not stop it, an empty asm
+// between them does not either -- the contraction happens in ptxas, seen in SASS as 18 -> 16 FMUL2 / FADD2), and it
+// does so in some copies of a loop body and not in others.  The scalar mul.rn.f32 is never contracted (PTX ISA).  Used
+// where one kernel STORES the product and another ACCUMULATES it and both must give the same bits (the l = 0 row of
+// the gather adjoint: open-chunk kernel + source_reduce against the closed-chunk half kernels).
+__device__ __forceinline__ float4 vmul_unfused(float4 a, float4 b) {
+    return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
+}
 // acc += a * b,  acc -= a * b  (elementwise; packed FFMA2)
 __device__ __forceinline__ void f4fmav(float4& acc, float4 a, float4 b) {
     const float2 lo = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(acc.x, acc.y));
@@ -111,6 +120,11 @@ __device__ __forceinline__ void f4fmav(float4& acc, float4 a, float4 b) {
     acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ void vfmav(float4& acc, float4 a, float4 b) { f4fmav(acc, a, b); }
+__device__ __forceinline__ D4 vmul_unfused(D4 a, D4 b) {
+    float4 t = vmul_unfused(a.d, b.v);
+    f4fmav(t, a.v, b.d);
+    return D4{vmul_unfused(a.v, b.v), t};
+}
 __device__ __forceinline__ void vfmav(D4& acc, D4 a, D4 b) {
     f4fmav(acc.v, a.v, b.v);
     f4fmav(acc.d, a.v, b.d);
@@ -196,6 +210,19 @@ template <> struct AP<float> {
     __host__ __device__ AP operator+(long long o) const {
         return AP{p ? p + o : nullptr, hi ? hi + o : nullptr, lo ? lo + o : nullptr};
     }
+    // format known at compile time (kernels instantiated per format: no uniform branch per store, and the address
+    // arithmetic of neighbouring stores folds into immediates)
+    template <bool PL> __device__ __forceinline__ void st4t(long long i, float4 x) const {
+        if constexpr (PL) {
+            uint2 h, l;
+            split4(x, h, l);
+            *reinterpret_cast<uint2*>(hi + i) = h;
+            *reinterpret_cast<uint2*>(lo + i) = l;
+        } else {
+            *reinterpret_cast<float4*>(p + i) = x;
+        }
+    }
+    __host__ __device__ bool planes() const { return hi != nullptr; }
     __device__ __forceinline__ void st4(long long i, float4 x) const {
         if (hi) {
             // (pairing lanes for one 16-byte store per lane instead of two 8-byte ones was measured: no gain)
@@ -215,6 +242,11 @@ template <> struct AP<D1> {
         v.st4(i, x.v);
         d.st4(i, x.d);
     }
+    template <bool PL> __device__ __forceinline__ void st4t(long long i, D4 x) const {
+        v.template st4t<PL>(i, x.v);
+        d.template st4t<PL>(i, x.d);
+    }
+    __host__ __device__ bool planes() const { return v.hi != nullptr; }
 };
 
 // occupancy hint: the float instantiations keep the register budgets of the hand-tuned float kernels

@@ -133,9 +133,11 @@ __device__ __forceinline__ S torque_load(GP<S> g_tau, long long e, int lane) {
 template <class S, class V>
 __device__ __forceinline__ void torque_commit(const TorqueAcc<V>& t, S scale, S old, GP<S> g_tau, long long e, int lane) {
     constexpr float SQ3 = 1.7320508075688772f;
-    const S tx = warp_sum(vhsum(t.x1) + SQ3 * vhsum(t.xs));
-    const S tz = warp_sum(vhsum(t.z1) + SQ3 * vhsum(t.zs));
-    if (lane < 2) g_tau.st(e * 4 + lane, old + scale * (lane == 0 ? tx : tz));
+    // explicit fused multiply-adds: the open-chunk and the closed-chunk kernels must round identically whatever the
+    // compiler would contract on its own (test_closed_chunks_equal_open_chunks compares them bit for bit)
+    const S tx = warp_sum(s_fma(cst<S>(SQ3), vhsum(t.xs), vhsum(t.x1)));
+    const S tz = warp_sum(s_fma(cst<S>(SQ3), vhsum(t.zs), vhsum(t.z1)));
+    if (lane < 2) g_tau.st(e * 4 + lane, s_fma(scale, lane == 0 ? tx : tz, old));
 }
 
 // scalars [LO, LO+N) of the Wigner record of edge e (D1 = 0..8, D2 = 9..33)
@@ -236,7 +238,7 @@ gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __re
 // adjoint: one warp per TARGET node of the chunk, looping over its CSR row.
 //   g_rad [E,1536] (A operand of the radial adjoint GEMM; never aliases rad);  G[e] = dL/dx[src] contribution [9,128] (l-primary);
 //   g_x[i] = sum over the row of the target-half contributions;  g_wig[e] += ...
-template <class S>
+template <class S, bool PL>
 __global__ void __launch_bounds__(256)
 gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __restrict__ src, GP<S> wig, GP<S> rad,
                          long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
@@ -293,14 +295,14 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
                 V ga = gbufs[a_buf(k)].ldg4(a_off(k) + half * C + lane * 4);
                 V rv = rad.ldg4(rp + r_off(k) + half * C);
                 const int grp_id = k < 3 ? k : (k == 3 || k == 5 ? 3 : (k == 4 || k == 6 ? 4 : 5));
-                g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(k)]));
-                gml[to_m(k)] = vmul(ga, rv);
+                vfmav(g_rad_v[grp_id], ga, yl[to_m(k)]);           // explicit FMA (never left to the contraction heuristics)
+                gml[to_m(k)] = k == 0 ? vmul_unfused(ga, rv) : vmul(ga, rv);   // row 0 is added as it is: see vmul_unfused
             }
 #pragma unroll
-            for (int q = 0; q < 3; ++q) g_rad.st4(rp + q * 256 + half * C, g_rad_v[q]);
-            g_rad.st4(rp + 768 + half * C, g_rad_v[3]);
-            g_rad.st4(rp + 1024 + half * C, g_rad_v[4]);
-            g_rad.st4(rp + 1280 + half * C, g_rad_v[5]);
+            for (int q = 0; q < 3; ++q) g_rad.template st4t<PL>(rp + q * 256 + half * C, g_rad_v[q]);
+            g_rad.template st4t<PL>(rp + 768 + half * C, g_rad_v[3]);
+            g_rad.template st4t<PL>(rp + 1024 + half * C, g_rad_v[4]);
+            g_rad.template st4t<PL>(rp + 1280 + half * C, g_rad_v[5]);
             torque_acc(tq, gml, yl);                 // <g_y, J_k y>,  y = D x
             V gx[9];
             rot_bwd(w, gml, gx);
@@ -326,7 +328,7 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 //   HALF = 1  one warp per target node i, over its in-edges  (CSR row):       g_x[i]  = sum of target-half terms
 //   HALF = 0  one warp per source node j, over its out-edges (sedge list):    g_x[j] += sum of source-half terms
 // Both add their share of dL/dD into g_wig[e]; HALF = 1 runs first, HALF = 0 second (fixed order: deterministic).
-template <int HALF, class S>
+template <int HALF, class S, bool PL>
 __global__ void __launch_bounds__(256)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
@@ -374,14 +376,14 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
             V ga = gbufs[a_buf(kk)].ldg4(a_off(kk) + HALF * C + lane * 4);
             V rv = rad.ldg4(rp + r_off(kk) + HALF * C);
             const int grp_id = kk < 3 ? kk : (kk == 3 || kk == 5 ? 3 : (kk == 4 || kk == 6 ? 4 : 5));
-            g_rad_v[grp_id] = vadd(g_rad_v[grp_id], vmul(ga, yl[to_m(kk)]));
-            gml[to_m(kk)] = vmul(ga, rv);
+            vfmav(g_rad_v[grp_id], ga, yl[to_m(kk)]);          // explicit FMA (never left to the contraction heuristics)
+            gml[to_m(kk)] = kk == 0 ? vmul_unfused(ga, rv) : vmul(ga, rv);   // row 0 is added as it is: see vmul_unfused
         }
 #pragma unroll
-        for (int q = 0; q < 3; ++q) g_rad.st4(rp + q * 256 + HALF * C, g_rad_v[q]);
-        g_rad.st4(rp + 768 + HALF * C, g_rad_v[3]);
-        g_rad.st4(rp + 1024 + HALF * C, g_rad_v[4]);
-        g_rad.st4(rp + 1280 + HALF * C, g_rad_v[5]);
+        for (int q = 0; q < 3; ++q) g_rad.template st4t<PL>(rp + q * 256 + HALF * C, g_rad_v[q]);
+        g_rad.template st4t<PL>(rp + 768 + HALF * C, g_rad_v[3]);
+        g_rad.template st4t<PL>(rp + 1024 + HALF * C, g_rad_v[4]);
+        g_rad.template st4t<PL>(rp + 1280 + HALF * C, g_rad_v[5]);
         torque_acc(tq, gml, yl);                     // <g_y, J_k y>,  y = D x
         V gx[9];
         rot_bwd(w, gml, gx);
@@ -594,7 +596,7 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
 }
 
 // adjoint, one warp per edge.  gZ* (A operands of the conv-2 adjoint GEMMs) never alias Z*.
-template <int MODE, class S>
+template <int MODE, class S, bool PL>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
                        long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
@@ -617,24 +619,24 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
     // t = D g serves all three outputs:  d/dz = s t (m-primary rows),  d/denv = scale <D^T z, g> = scale <z, t>,
     // torque = - s <t, J_k z>
     rot_fwd(w, g, t);
-    S part = cst<S>(0.f);
+    V pacc = vzero<V>();
 #pragma unroll
-    for (int r = 0; r < 9; ++r) part = part + vdot(t[r], zl[r]);
-    part = warp_sum(part);
+    for (int r = 0; r < 9; ++r) vfmav(pacc, t[r], zl[r]);
+    S part = warp_sum(vhsum(pacc));
     if (lane == 0) g_env.st(e, genv_old + part * scale);
     const long long o0 = (long long)el * 384 + lane * 4;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) gZ0.st4(o0 + k * 128, vscale(t[to_m(k)], s));
+    for (int k = 0; k < 3; ++k) gZ0.template st4t<PL>(o0 + k * 128, vscale(t[to_m(k)], s));
     if (MODE == 0) {
         const long long o1 = (long long)el * 512 + lane * 4;
         const long long o2 = (long long)el * 256 + lane * 4;
 #pragma unroll
         for (int l = 0; l < 2; ++l) {
-            gZ1.st4(o1 + l * 128, vscale(t[to_m(3 + l)], s));
-            gZ1.st4(o1 + 256 + l * 128, vscale(t[to_m(5 + l)], s));
+            gZ1.template st4t<PL>(o1 + l * 128, vscale(t[to_m(3 + l)], s));
+            gZ1.template st4t<PL>(o1 + 256 + l * 128, vscale(t[to_m(5 + l)], s));
         }
-        gZ2.st4(o2, vscale(t[to_m(7)], s));
-        gZ2.st4(o2 + 128, vscale(t[to_m(8)], s));
+        gZ2.template st4t<PL>(o2, vscale(t[to_m(7)], s));
+        gZ2.template st4t<PL>(o2 + 128, vscale(t[to_m(8)], s));
     }
     // torque of the rotate-back: - s <D g, J_k z>  (after the stores: they do not wait for the reductions)
     TorqueAcc<V> tq = torque_zero<V>();
@@ -656,8 +658,12 @@ void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<
                                 int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
                                 GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
-    gather_rotate_bwd_kernel<S><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes, gA0,
-                                                                   gA1, gA2, g_rad, G, g_x, g_wig);
+    if (g_rad.planes())
+        gather_rotate_bwd_kernel<S, true><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes,
+                                                                             gA0, gA1, gA2, g_rad, G, g_x, g_wig);
+    else
+        gather_rotate_bwd_kernel<S, false><<<(n_nodes + 7) / 8, 256, 0, st>>>(x, row_ptr, src, wig, rad, e0, node0, n_nodes,
+                                                                              gA0, gA1, gA2, g_rad, G, g_x, g_wig);
     UMAB_LAUNCH_CHECK();
 }
 // closed chunks: target halves over the CSR rows, then source halves over the out-edge lists (no G, no source_reduce)
@@ -668,11 +674,19 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
     if (n_nodes <= 0) return;
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
     const dim3 grid((n_nodes + 7) / 8);
-    gather_rotate_bwd_half_kernel<1, S><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2,
-                                                             g_rad, g_x, g_wig);
-    UMAB_LAUNCH_CHECK();
-    gather_rotate_bwd_half_kernel<0, S><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1, gA2, g_rad,
-                                                             g_x, g_wig);
+    if (g_rad.planes()) {
+        gather_rotate_bwd_half_kernel<1, S, true><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+                                                                        gA1, gA2, g_rad, g_x, g_wig);
+        UMAB_LAUNCH_CHECK();
+        gather_rotate_bwd_half_kernel<0, S, true><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+                                                                        gA2, g_rad, g_x, g_wig);
+    } else {
+        gather_rotate_bwd_half_kernel<1, S, false><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+                                                                         gA1, gA2, g_rad, g_x, g_wig);
+        UMAB_LAUNCH_CHECK();
+        gather_rotate_bwd_half_kernel<0, S, false><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+                                                                         gA2, g_rad, g_x, g_wig);
+    }
     UMAB_LAUNCH_CHECK();
 }
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st) {
@@ -717,10 +731,16 @@ void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int*
                               GP<S> g_wig, cudaStream_t st) {
     if (n_e <= 0) return;
     dim3 grid((n_e + 7) / 8);
-    if (mode == 0)
-        rotate_back_bwd_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
-    else
-        rotate_back_bwd_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, gZ2, g_env, g_wig);
+#define UMAB_RBB(MODE, PL)                                                                                           \
+    rotate_back_bwd_kernel<MODE, S, PL><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, \
+                                                               gZ2, g_env, g_wig)
+    const bool pl = gZ0.planes();
+    if (mode == 0) {
+        if (pl) UMAB_RBB(0, true); else UMAB_RBB(0, false);
+    } else {
+        if (pl) UMAB_RBB(1, true); else UMAB_RBB(1, false);
+    }
+#undef UMAB_RBB
     UMAB_LAUNCH_CHECK();
 }
 

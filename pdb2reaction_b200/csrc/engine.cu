@@ -456,6 +456,16 @@ struct umab_engine {
         UMAB_CUDA(cudaMemcpyAsync(slot.first.p, p, numel * 4, cudaMemcpyDeviceToDevice, st));
     }
 
+    // debug: a per-chunk tensor copied into its rows [row0, row0 + rows) of a whole-batch debug tensor
+    void save_dbg_rows(const std::string& name, const void* p, size_t rows, size_t width, size_t row0, size_t total_rows,
+                       cudaStream_t st) {
+        if (!cfg.debug) return;
+        auto& slot = dbg[name];
+        slot.first.ensure(total_rows * width * 4);
+        slot.second = total_rows * width;
+        UMAB_CUDA(cudaMemcpyAsync(slot.first.f() + row0 * width, p, rows * width * 4, cudaMemcpyDeviceToDevice, st));
+    }
+
     // ------------------------------------------------------------------ graph
     // fcap > 0: sync-free build on edge arrays of that capacity (see the members above); 0: read row_ptr back
     void build_graph(const float* pos, int nimg, cudaStream_t st, long long fcap = 0) {
@@ -749,14 +759,28 @@ struct umab_engine {
         timed(P_ROTBACK_BWD, P * (c.n_e * (2 * ZW * 4.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
             launch_rotate_back_bwd_t<S>(0, b.z0, b.z1, b.z2, tgt.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0, c.n_e, g_out,
                                         b.gz0, b.gz1, b.gz2, gp<S>(g_env), gp<S>(g_wig), st); });
+        if (cfg.debug && !use_tc()) {
+            const std::string p = "bwd.l" + std::to_string(layer) + ".";
+            save_dbg_rows(p + "gz0", plane(b.gb0, 0) /* same memory as gz0 in fp32 mode */, c.n_e, 384, c.e0, n_edges, st);
+        }
         mm_ap<S>(b.gz0, w.c2m0_t, 384, 384, b.gb0, 384, c.n_e, nullptr, st);
         mm_ap<S>(b.gz1, w.c2m1_t, 512, 512, b.gb1, 512, c.n_e, nullptr, st);
         mm_ap<S>(b.gz2, w.c2m2_t, 256, 256, b.gb2, 256, c.n_e, nullptr, st);
         timed(P_COMBINE_BWD, P * c.n_e * (YW * 4.0 * 2 + 4608.0), st, [&] {
             launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.gb0, b.gb1, b.gb2, b.gy0, b.gy1, b.gy2, st); });
+        if (cfg.debug && !use_tc()) {
+            const std::string p = "bwd.l" + std::to_string(layer) + ".";
+            save_dbg_rows(p + "gb0", plane(b.gb0, 0), c.n_e, 384, c.e0, n_edges, st);
+            save_dbg_rows(p + "gy0", plane(b.gy0, 0).p, c.n_e, 640, c.e0, n_edges, st);
+        }
         mm_ap<S>(b.gy0, w.c1m0_t, 768, 640, b.ga0, 768, c.n_e, nullptr, st);
         mm_ap<S>(b.gy1, w.c1m1_t, 1024, 512, b.ga1, 1024, c.n_e, nullptr, st);
         mm_ap<S>(b.gy2, w.c1m2_t, 512, 256, b.ga2, 512, c.n_e, nullptr, st);
+        if (cfg.debug && !use_tc()) {
+            const std::string p = "bwd.l" + std::to_string(layer) + ".";
+            save_dbg_rows(p + "ga0", plane(b.ga0, 0), c.n_e, 768, c.e0, n_edges, st);
+            save_dbg_rows(p + "rad", plane(b.rad, 0), c.n_e, 1536, c.e0, n_edges, st);
+        }
         if (chunks_closed)
             timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 6 * 144.0 + 8.0) + c.n_nodes * 5 * 4608.0), st, [&] {
                 launch_gather_rotate_bwd_closed_t<S>(n1, row_ptr.i(), sptr.i(), sedge.i(), gp<S>(wig), b.rad, c.e0, c.node0,

@@ -328,13 +328,19 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 //   HALF = 1  one warp per target node i, over its in-edges  (CSR row):       g_x[i]  = sum of target-half terms
 //   HALF = 0  one warp per source node j, over its out-edges (sedge list):    g_x[j] += sum of source-half terms
 // Both add their share of dL/dD into g_wig[e]; HALF = 1 runs first, HALF = 0 second (fixed order: deterministic).
+#ifndef UMAB_HALF_NW
+#define UMAB_HALF_NW 8          // warps (nodes) per CTA of the half kernels
+#define UMAB_HALF_MINB 1        // CTAs per SM the register budget is sized for
+// measured on one box (tools/gpu_ab_libs.sh): 8 warps x 1 CTA (204 / 238 registers, no spills) 60.0 / 60.7 ms per C4 step;
+// 6 x 2 and 4 x 3 (168 registers, 200-280 B of spills, 12 resident warps) 70.1 / 69.9 and 69.6 / 68.4 ms
+#endif
 template <int HALF, class S, bool PL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(UMAB_HALF_NW * 32, UMAB_HALF_MINB)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
                               GP<S> g_x, GP<S> g_wig) {
     using V = typename VecOf<S>::type;
-    const int nl = blockIdx.x * 8 + threadIdx.x / 32;
+    const int nl = blockIdx.x * UMAB_HALF_NW + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (nl >= n_nodes) return;
     const int i = node0 + nl;
@@ -673,18 +679,18 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
                                        GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
     if (n_nodes <= 0) return;
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
-    const dim3 grid((n_nodes + 7) / 8);
+    const dim3 grid((n_nodes + UMAB_HALF_NW - 1) / UMAB_HALF_NW);
     if (g_rad.planes()) {
-        gather_rotate_bwd_half_kernel<1, S, true><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+        gather_rotate_bwd_half_kernel<1, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
                                                                         gA1, gA2, g_rad, g_x, g_wig);
         UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, true><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+        gather_rotate_bwd_half_kernel<0, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
                                                                         gA2, g_rad, g_x, g_wig);
     } else {
-        gather_rotate_bwd_half_kernel<1, S, false><<<grid, 256, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+        gather_rotate_bwd_half_kernel<1, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
                                                                          gA1, gA2, g_rad, g_x, g_wig);
         UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, false><<<grid, 256, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+        gather_rotate_bwd_half_kernel<0, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
                                                                          gA2, g_rad, g_x, g_wig);
     }
     UMAB_LAUNCH_CHECK();

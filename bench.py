@@ -56,6 +56,9 @@ def parse():
                    help="measure BASELINE.json's second metric instead: wall time of the full FD Hessian of the C3 "
                         "cluster (--hessian-atoms), column blocks sharded over the N ranks, one all_gather")
     p.add_argument("--hessian-atoms", type=int, default=500)
+    p.add_argument("--hessian-mode", choices=["fd", "analytic"], default="fd",
+                   help="fd: the reference's default mode (1 + 6N force evaluations); analytic: the mode BASELINE configs[2] "
+                        "names (3N dual-number forward + backward passes)")
     return p.parse_args()
 
 
@@ -238,13 +241,16 @@ def run_hessian(args, world, rank, local):
     import torch.distributed as dist
     from pdb2reaction_b200 import synth, uma_pysis
     from pdb2reaction_b200.shims import ANG2BOHR
-    from pdb2reaction_b200.sharding import sharded_fd_hessian
+    from pdb2reaction_b200.sharding import sharded_analytic_hessian, sharded_fd_hessian
+    analytic = args.hessian_mode == "analytic"
+    hess = sharded_analytic_hessian if analytic else sharded_fd_hessian
     n = args.hessian_atoms
     elem, coords = synth.make_cluster(n, 3)
     c = (coords * ANG2BOHR).reshape(-1)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}")
+        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}",
+                         hessian_calc_mode="Analytical" if analytic else "FiniteDifference")
         calc.get_forces(elem, c)                                  # engine build + warm-up
 
     def barrier():
@@ -261,7 +267,7 @@ def run_hessian(args, world, rank, local):
     launches0 = eng.stats()["kernel_launches"]
     t0 = time.perf_counter()
     for _ in range(steps):
-        r = sharded_fd_hessian(calc, elem, c)
+        r = hess(calc, elem, c)
         hnorm = float(r["hessian"].abs().max())                   # D2H read of the result
     barrier()
     dt = (time.perf_counter() - t0) / steps
@@ -275,13 +281,18 @@ def run_hessian(args, world, rank, local):
         h = r["hessian"]
         emit({"metric": "Hessian wall-time", "value": dt, "unit": "s", "n_gpus": world, "steps": steps, "warmup": 1,
               "ms_per_step": 1e3 * dt, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-              "dtype": "f32 forces (bf16x3 split tensor-core GEMMs), f64 Hessian assembly", "data": "synthetic",
-              "config": {"workload": f"C3: full FiniteDifference Hessian of a {n}-atom cluster (BASELINE.json configs[2]), "
-                                     f"{3 * n} columns = {1 + 6 * n} force evaluations, column blocks sharded over {world} GPU(s)",
+              "dtype": ("f32 dual numbers (bf16x3 split tensor-core GEMMs per plane), f32 Hessian as the reference's autograd mode"
+                        if analytic else "f32 forces (bf16x3 split tensor-core GEMMs), f64 Hessian assembly"), "data": "synthetic",
+              "config": {"workload": (f"C3: full ANALYTIC Hessian of a {n}-atom cluster (BASELINE.json configs[2]), {3 * n} columns = "
+                                      f"{3 * n} dual-number forward + backward passes, column blocks sharded over {world} GPU(s)"
+                                      if analytic else
+                                      f"C3: full FiniteDifference Hessian of a {n}-atom cluster (BASELINE.json configs[2]), "
+                                      f"{3 * n} columns = {1 + 6 * n} force evaluations, column blocks sharded over {world} GPU(s)"),
+                         "hessian_calc_mode": "Analytical" if analytic else "FiniteDifference",
                          "n_atoms": n, "columns": 3 * n, "collective": "none (1 GPU)" if world == 1 else "one all_gather of the column blocks"},
-              "columns_per_s": 3 * n / dt, "force_evals_per_s": (1 + 6 * n) / dt,
-              "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int((1 + 6 * n) * n * 12 // world),
-                      "d2h_bytes_per_step": 8, "api": "sharding.sharded_fd_hessian(uma_pysis, elem, coords_bohr) "
+              "columns_per_s": 3 * n / dt, "force_evals_per_s": (None if analytic else (1 + 6 * n) / dt),
+              "e2e": {"value": dt, "unit": "s", "h2d_bytes_per_step": int(n * 12 if analytic else (1 + 6 * n) * n * 12 // world),
+                      "d2h_bytes_per_step": 8, "api": f"sharding.{hess.__name__}(uma_pysis, elem, coords_bohr) "
                       "(= uma_pysis.get_hessian at N = 1): host coordinates in, Hessian on the device + one scalar read back"},
               "gpu_launches": int(launches), "clocks": clocks,
               "hessian": {"shape": list(h.shape), "dtype": str(h.dtype), "max_abs": hnorm,
@@ -327,7 +338,8 @@ def main():
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}")       # the public API object (e2e path)
+        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}",
+                         hessian_calc_mode="Analytical" if analytic else "FiniteDifference")       # the public API object (e2e path)
         calc._ensure_core(elem)
     eng = calc._core.backend.engines[0]
     pos_dev = torch.from_numpy(imgs.astype(np.float32)).cuda()

@@ -451,9 +451,17 @@ class uma_pysis(Calculator):
         active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
         res0 = core.compute(coord_ang, forces=True)
         cols = core.backend.hessian_columns(coord_ang, active_dof)            # [n_active_dof, 3N] fp32
+        return self._assemble_analytic_hessian(res0, torch.from_numpy(cols).to(dev), n_atoms)
+
+    def _assemble_analytic_hessian(self, res0, cols: torch.Tensor, n_atoms: int):
+        """Active columns [n_active_dof, 3N] (fp32, on the compute device) -> the (N,3,N,3) / (Na,3,Na,3) tensor of
+        ``_build_analytic_hessian`` (shared with ``sharding.sharded_analytic_hessian``: same bits)."""
+        dev = self._core.device
+        dof = 3 * n_atoms
+        active_atoms, active_dof, _ = self._active_and_frozen_dof_idx(n_atoms)
         hmat = torch.zeros((dof, dof), device=dev, dtype=torch.float32)       # model dtype, as the reference
         idx = torch.as_tensor(active_dof, device=dev, dtype=torch.long)
-        hmat[:, idx] = torch.from_numpy(cols).to(dev).T                       # frozen columns stay 0 (:589-591)
+        hmat[:, idx] = cols.T                                                 # frozen columns stay 0 (:589-591)
         if self.return_partial_hessian:
             hmat = hmat.index_select(0, idx).index_select(1, idx)
             na = len(active_atoms)

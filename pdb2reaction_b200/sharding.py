@@ -8,11 +8,13 @@ lives on rank 0) sees the whole string -- the new meaning of the reference's ``w
 (``pdb2reaction/uma_pysis.py:52-63, 213-242``; there: Ray actors + graph parallelism over ONE
 structure).
 
-Hessian column blocks shard the same way (BASELINE.json configs[2]): ``sharded_fd_hessian`` gives every rank a
-contiguous block of the active columns and ends in ONE all_gather of the blocks.
+Hessian column blocks shard the same way (BASELINE.json configs[2]): ``sharded_analytic_hessian`` (dual-number columns,
+the mode configs[2] names) and ``sharded_fd_hessian`` (the reference's default mode) give every rank a contiguous block
+of the active columns and end in ONE all_gather of the blocks.
 
 Three drivers use this module:
-* ``sharded_fd_hessian``: one process per GPU under ``torchrun`` (bench.py ``--hessian --gpus N``);
+* ``sharded_analytic_hessian`` / ``sharded_fd_hessian``: one process per GPU under ``torchrun`` (bench.py ``--hessian
+  [--hessian-mode analytic|fd] --gpus N``);
 * ``CudaBackend`` (calculator.py): one process, one host thread per GPU, no collective at all;
 * ``SpmdEvaluator``: one process per GPU under ``torchrun`` (bench.py ``--gpus N``), NCCL
   all-gather over NVLink (gloo on CPU in the tests).
@@ -172,3 +174,46 @@ def sharded_fd_hessian(calc, elem, coords_bohr, group: Optional[dist.ProcessGrou
     f_ev = calc._zero_frozen_forces_ev(res0["forces"])
     return {"energy": calc._au_energy(res0["energy"]), "forces": calc._au_forces(f_ev),
             "hessian": calc._au_hessian(calc._finish_fd_hessian(hmat, n_atoms))}
+
+
+def sharded_analytic_hessian(calc, elem, coords_bohr, group: Optional[dist.ProcessGroup] = None):
+    """``calc.get_hessian(elem, coords)`` in Analytical mode (reference ``uma_pysis.py:394-415``; BASELINE.json
+    configs[2]: "full analytic Hessian, column blocks sharded across GPUs") with the ACTIVE COLUMNS sharded over the
+    ranks of ``group`` (one process per GPU): rank r runs the dual-number forward + backward passes of its contiguous
+    block of active degrees of freedom on its own device (``backend.hessian_columns``), ONE all_gather of the column
+    blocks (``[cols_r, 3N]`` fp32 each) gives every rank all columns, and the calculator's own assembly / trim /
+    symmetrise / unit / dtype formatting follows (``_assemble_analytic_hessian``, ``_au_hessian``; reference
+    ``:515-551, :569-592``).  Same result bits as the single-process ``get_hessian``.  Unlike the reference
+    (``:737``), more than one worker does not force the finite-difference mode."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    calc._ensure_core(elem)
+    core = calc._core
+    if not hasattr(core.backend, "hessian_columns"):
+        raise RuntimeError("sharded_analytic_hessian: this backend has no analytic Hessian columns")
+    coord_ang = calc._coords_ang(coords_bohr)
+    n_atoms = coord_ang.shape[0]
+    dof = 3 * n_atoms
+    _, active_dof, _ = calc._active_and_frozen_dof_idx(n_atoms)
+    res0 = core.compute(coord_ang, forces=True)
+    bounds = shard_bounds(len(active_dof), world)
+    lo, hi = bounds[rank]
+    dev = core.device if (world == 1 or dist.get_backend(group) == "nccl") else torch.device("cpu")
+    if hi > lo:
+        mine = torch.from_numpy(np.ascontiguousarray(core.backend.hessian_columns(coord_ang, active_dof[lo:hi]),
+                                                     dtype=np.float32)).to(dev)
+    else:
+        mine = torch.zeros((0, dof), dtype=torch.float32, device=dev)
+    if world > 1:
+        cap = max(h - l for l, h in bounds)
+        rec = torch.zeros((cap, dof), dtype=torch.float32, device=dev)
+        rec[: hi - lo] = mine
+        out = torch.empty((world * cap, dof), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(out, rec, group=group)              # the ONE collective of a Hessian
+        cols = torch.cat([out[r * cap: r * cap + (h - l)] for r, (l, h) in enumerate(bounds)])
+    else:
+        cols = mine
+    res = calc._assemble_analytic_hessian(res0, cols.to(core.device), n_atoms)
+    f_ev = calc._zero_frozen_forces_ev(res["forces"])
+    return {"energy": calc._au_energy(res["energy"]), "forces": calc._au_forces(f_ev),
+            "hessian": calc._au_hessian(res["hessian"])}

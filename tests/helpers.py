@@ -44,3 +44,10 @@ class SpringBackend:
         x = torch.tensor(np.asarray(coord_ang, dtype=np.float64))
         h = torch.autograd.functional.hessian(lambda v: self._e(v.view(-1, 3)), x.reshape(-1))
         return h.numpy()
+
+    def hessian_columns(self, coord_ang, dofs):
+        """Analytic-mode stand-in of ``CudaBackend.hessian_columns``: rows k of the exact Hessian at the fp32-rounded
+        geometry, as float32 [len(dofs), 3N]."""
+        h = self.hessian(np.asarray(coord_ang, dtype=np.float32).astype(np.float64))
+        return np.ascontiguousarray(h[[int(k) for k in dofs]], dtype=np.float32)
+

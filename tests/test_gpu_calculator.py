@@ -86,6 +86,21 @@ def test_analytic_hessian_columns_match_oracle_double_backward(built_lib, small_
     assert np.abs(hf[np.ix_(ad, ad)] - 0.5 * (h_ref + h_ref.T)[np.ix_(ad, ad)]).max() < 2e-4 * scale
 
 
+def test_sharded_analytic_hessian_equals_get_hessian_on_one_rank(built_lib, small_model):
+    """sharding.sharded_analytic_hessian (bench.py --hessian --hessian-mode analytic) on the CUDA backend, one rank:
+    the same bits as uma_pysis.get_hessian(hessian_calc_mode="Analytical"), also with frozen atoms and the active block
+    (the world-2 gather is covered by the gloo test in test_sharding.py)."""
+    from pdb2reaction_b200.sharding import sharded_analytic_hessian
+    elem, coords = synth.make_cluster(12, 5)
+    for kw in (dict(), dict(freeze_atoms=[0, 7]), dict(freeze_atoms=[0, 7], return_partial_hessian=True)):
+        a = uma_pysis(model="test-4x", hessian_calc_mode="Analytical", out_hess_torch=True, **kw).get_hessian(
+            elem, coords * ANG2BOHR)
+        b = sharded_analytic_hessian(uma_pysis(model="test-4x", hessian_calc_mode="Analytical", out_hess_torch=True, **kw),
+                                     elem, coords * ANG2BOHR)
+        assert torch.equal(a["hessian"], b["hessian"]) and a["energy"] == b["energy"]
+        assert np.array_equal(a["forces"], b["forces"])
+
+
 def test_forces_jvp_matches_central_difference_of_cuda_forces(built_lib, state4, arch4):
     from pdb2reaction_b200.engine import UmabEngine
     elem, imgs = synth.make_string(200, 2, 17)

@@ -93,6 +93,48 @@ def _hess_worker(rank, world, port, frozen, partial, q):
         dist.destroy_process_group()
 
 
+def _ahess_worker(rank, world, port, frozen, partial, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from helpers import SpringBackend
+    from pdb2reaction_b200 import uma_pysis
+    from pdb2reaction_b200.sharding import sharded_analytic_hessian
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        elem = ["C", "H", "H", "O", "N"]
+        x = np.array([[0, 0, 0], [1.1, 0, 0], [0, 1.0, 0.2], [0.3, -0.9, 0.8], [-1.0, 0.2, 0.5]]) / 0.529177210903
+        kw = dict(freeze_atoms=frozen, return_partial_hessian=partial, out_hess_torch=True, hessian_calc_mode="Analytical")
+        full = uma_pysis(_backend=SpringBackend(), **kw).get_hessian(elem, x.reshape(-1))
+        shard = sharded_analytic_hessian(uma_pysis(_backend=SpringBackend(), **kw), elem, x.reshape(-1))
+        ok = (torch.equal(full["hessian"], shard["hessian"]) and full["energy"] == shard["energy"]
+              and np.array_equal(full["forces"], shard["forces"]))
+        q.put((rank, bool(ok), tuple(shard["hessian"].shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("frozen,partial,shape", [([], False, (15, 15)), ([1, 3], False, (15, 15)), ([0, 1, 2, 4], True, (3, 3))])
+def test_sharded_analytic_hessian_gloo_world2(frozen, partial, shape):
+    """Analytic mode (BASELINE configs[2]): column blocks sharded over two ranks + one all_gather == the single-process
+    ``get_hessian(hessian_calc_mode="Analytical")``, bit for bit, including frozen columns, the active-block reduction
+    and a rank with fewer columns than the other (3 active columns over 2 ranks)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ahess_worker, args=(r, 2, port, frozen, partial, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, shp in res:
+        assert ok and shp == shape
+
+
 @pytest.mark.parametrize("frozen,partial,shape", [([], False, (15, 15)), ([1, 3], False, (15, 15)), ([0, 1, 2, 4], True, (3, 3))])
 def test_sharded_fd_hessian_gloo_world2(frozen, partial, shape):
     """Column blocks sharded over two ranks + one all_gather == the single-process Hessian, bit for bit

@@ -266,13 +266,19 @@ class CudaBackend:
             with torch.cuda.device(dev):
                 per = max(1, eng.images_per_call(True) // 2)
                 p1 = torch.from_numpy(pos32).to(dev)
-                for s in range(lo, hi, per):
-                    ks = dofs[s:min(hi, s + per)]
-                    pos = p1.unsqueeze(0).expand(len(ks), n, 3).contiguous()
-                    tan = torch.zeros(len(ks), 3 * n, device=dev, dtype=torch.float32)
-                    tan[torch.arange(len(ks), device=dev), torch.as_tensor(ks, device=dev)] = 1.0
-                    _, df = eng.forces_jvp(pos, tan.view(len(ks), n, 3))
-                    out[s:s + len(ks)] = (-df).reshape(len(ks), -1).cpu().numpy()
+                # every image of these batches sits at the SAME geometry: the engine runs the value-plane GEMMs on one
+                # image and copies the block to the others (verified on the device per call; identical result bits)
+                eng.set_option("jvp_shared_base", 1)
+                try:
+                    for s in range(lo, hi, per):
+                        ks = dofs[s:min(hi, s + per)]
+                        pos = p1.unsqueeze(0).expand(len(ks), n, 3).contiguous()
+                        tan = torch.zeros(len(ks), 3 * n, device=dev, dtype=torch.float32)
+                        tan[torch.arange(len(ks), device=dev), torch.as_tensor(ks, device=dev)] = 1.0
+                        _, df = eng.forces_jvp(pos, tan.view(len(ks), n, 3))
+                        out[s:s + len(ks)] = (-df).reshape(len(ks), -1).cpu().numpy()
+                finally:
+                    eng.set_option("jvp_shared_base", 0)
 
         if self._pool is None:
             run(0)

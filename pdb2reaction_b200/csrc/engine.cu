@@ -233,6 +233,35 @@ struct umab_engine {
     bool nosync_enabled() const { return opt_nosync; }
     bool graphs_enabled() const { return opt_graphs; }
     long long graph_replays = 0, graph_captures = 0, overflow_retries = 0, fast_calls = 0;
+    // Hessian columns of ONE base geometry (umab_set_option "jvp_shared_base"; calculator.hessian_columns): every image
+    // of the dual-number batch has the same positions, so the VALUE plane of every tensor is the same for all images.
+    // The value-plane GEMMs then run on the rows of ONE image and the result block is copied to the others (a streaming
+    // write instead of a GEMM); the tangent planes and all elementwise kernels are untouched, so the result bits are the
+    // same as without the option (GEMM rows are independent of M).  Checked on the device per call (same_images).
+    bool opt_shared_base = false;
+    bool dedupe = false;                               // this call: positions of all images verified identical
+    long long rep_rows = 0;                            // rows per image of the GEMMs being issued (0: do not de-duplicate)
+    long long e_img = 0;                               // edges per image (dedupe)
+    long long dedupe_gemms = 0;                        // value-plane GEMMs run on one image (umab_get_option "dedupe_gemms")
+    DevBuf same_flag;
+    // value-plane GEMM on one image + replication, or the plain GEMM
+    void gemm_plane(GemmArgs& g, int k, long long M, long long block_ld, cudaStream_t st) {
+        if (k == 0 && rep_rows > 0 && M > rep_rows && M % rep_rows == 0 && !g.gate) {
+            g.M = (int)rep_rows;
+            gemm(g, st);
+            launch_replicate_block(g.Cmat, rep_rows * block_ld, (int)(M / rep_rows), st);
+            ++dedupe_gemms;
+        } else {
+            g.M = (int)M;
+            gemm(g, st);
+        }
+    }
+    struct RepScope {                                  // rows per image inside a chunk loop, restored on exit
+        umab_engine* e; long long saved;
+        RepScope(umab_engine* e_, long long rows) : e(e_), saved(e_->rep_rows) { e->rep_rows = rows; }
+        ~RepScope() { e->rep_rows = saved; }
+    };
+    long long chunk_rep_rows() const { return dedupe && chunks_closed ? e_img : 0; }
     std::vector<Chunk> chunks;
     bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
     static bool store_radial_enabled() {               // UMAB_STORE_RADIAL=0: recompute the radial MLP in the backward (A/B)
@@ -396,8 +425,8 @@ struct umab_engine {
             GemmArgs g;
             g.A = plane(A, k); g.lda = lda; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
             g.bias = k == 0 ? bias : nullptr;
-            g.M = (int)M; g.N = N; g.K = K; g.accumulate = accumulate;
-            gemm(g, st);
+            g.N = N; g.K = K; g.accumulate = accumulate;
+            gemm_plane(g, k, M, ldc, st);
         }
     }
     // same with an A operand written by an elementwise kernel (fp32, or bf16 hi/lo planes for the TMA-fed GEMM)
@@ -410,8 +439,8 @@ struct umab_engine {
             GemmArgs g;
             g.A = a.p; g.A_hi = a.hi; g.A_lo = a.lo; g.lda = K; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
             g.bias = k == 0 ? bias : nullptr;
-            g.M = (int)M; g.N = N; g.K = K; g.accumulate = 0;
-            gemm(g, st);
+            g.N = N; g.K = K; g.accumulate = 0;
+            gemm_plane(g, k, M, ldc, st);
         }
     }
     // conv-1 m != 0 GEMM with the gate applied in the epilogue (float, CTA-pair kernel): C = A W^T (fp32, kept) and
@@ -434,10 +463,10 @@ struct umab_engine {
             g.W = Wt; g.ldw = K; g.strideW = (long long)Nout * K;
             g.Cmat = plane(Cm, k); g.ldc = 9LL * Nout; g.strideC = Nout;
             g.bias = k == 0 ? bias : nullptr; g.bias_first_batch_only = 1;
-            g.M = n_nodes; g.N = Nout; g.K = K; g.batch = 9; g.accumulate = accumulate;
+            g.N = Nout; g.K = K; g.batch = 9; g.accumulate = accumulate;
             const int lsel[9] = {0, 1, 1, 1, 2, 2, 2, 2, 2};
             for (int i = 0; i < 9; ++i) g.wsel[i] = lsel[i];
-            gemm(g, st);
+            gemm_plane(g, k, n_nodes, 9LL * Nout, st);
         }
     }
     template <class S> void zero(const TBuf& b, size_t bytes, cudaStream_t st) {
@@ -832,8 +861,24 @@ struct umab_engine {
     void evaluate_impl(GP<S> pos, int nimg, double* energy_dev, GP<S> forces, cudaStream_t st) {
         if (!finalized) throw CudaError("umab_finalize_weights has not been called");
         if (resolve_status()) { /* an unchecked overflow of an earlier device-pointer call: the history has been updated */ }
-        const long long fcap = fast_capacity<S>(nimg);
+        const bool want_shared = std::is_same<S, D1>::value && opt_shared_base && nimg > 1;
+        const long long fcap = want_shared ? 0 : fast_capacity<S>(nimg);      // the de-duplication needs the edge counts on the host
         timed(P_GRAPH, (double)nimg * n_atoms * 12.0, st, [&] { build_graph(plane(pos, 0), nimg, st, fcap); });
+        dedupe = false; rep_rows = 0; e_img = 0;
+        if (want_shared) {
+            same_flag.ensure(sizeof(int));
+            launch_same_images(plane(pos, 0), (long long)n_atoms * 3, nimg, same_flag.i(), st);
+            int differ = 1;
+            UMAB_CUDA(cudaMemcpyAsync(&differ, same_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            UMAB_CUDA(cudaStreamSynchronize(st));
+            e_img = h_pinned[n_atoms];
+            bool same = differ == 0 && e_img > 0;
+            for (int b = 1; b < nimg && same; ++b)
+                same = (long long)h_pinned[(b + 1) * n_atoms] - h_pinned[b * n_atoms] == e_img;
+            dedupe = same;
+            rep_rows = dedupe ? n_atoms : 0;          // node-level GEMMs; the chunk loops set the edge-level value
+        }
+        struct DedupeOff { umab_engine* e; ~DedupeOff() { e->dedupe = false; e->rep_rows = 0; } } dedupe_off{this};
         const int L = cfg.num_layers;
         const size_t ne = (size_t)std::max<long long>(n_edges, 1);
         const size_t nf = (size_t)n_nodes * 9 * C * sizeof(float);
@@ -874,6 +919,7 @@ struct umab_engine {
         launch_embed(sphere_emb, csd, zt.i(), n_nodes, xs[0].v.f(), st);
         if (std::is_same<S, D1>::value) UMAB_CUDA(cudaMemsetAsync(xs[0].d.p, 0, nf, st));
         for (const Chunk& c : chunks) {
+            RepScope rs(this, chunk_rep_rows());
             const EB<S> b = bufs_for<S>(-1, c);
             radial_fwd<S>(ed_rad, c, b, st);
             launch_rotate_back_reduce_t<S>(1, b.rad, gnull<S>(), gnull<S>(), row_ptr.i(), gp<S>(wig), gp<S>(env),
@@ -891,6 +937,7 @@ struct umab_engine {
             launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);
             save_dbg("l" + std::to_string(l) + ".n1", nbuf.v.p, (size_t)n_nodes * 9 * C, st);
             for (const Chunk& c : chunks) {
+                RepScope rs(this, chunk_rep_rows());
                 edge_fwd_chunk<S>(w, gp<S>(nbuf), c, l, true, st);
                 const EB<S> b = bufs_for<S>(l, c);
                 timed(P_ROTBACK, planes<S>() * (c.n_e * (ZW * 4.0 + 148.0) + c.n_nodes * 9216.0), st, [&] {
@@ -944,7 +991,10 @@ struct umab_engine {
             launch_rms_bwd_t<S>(gp<S>(x1s[l]), w.n2w, gp<S>(gn), gp<S>(gx), n_nodes, gp<S>(gx1), st);   // g_x1
             // Edgewise adjoint
             launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);         // recompute n1
-            for (const Chunk& c : chunks) edge_bwd_chunk<S>(w, gp<S>(nbuf), c, l, gp<S>(gx1), gp<S>(gn), st);
+            for (const Chunk& c : chunks) {
+                RepScope rs(this, chunk_rep_rows());
+                edge_bwd_chunk<S>(w, gp<S>(nbuf), c, l, gp<S>(gx1), gp<S>(gn), st);
+            }
             if (!chunks_closed) timed(P_SRC_REDUCE, planes<S>() * (n_edges * 4612.0 + n_nodes * 9216.0), st, [&] {
                 for (int k = 0; k < planes<S>(); ++k)
                     launch_source_reduce(plane(gp<S>(Gbuf), k), sptr.i(), sedge.i(), n_nodes, plane(gp<S>(gn), k), st); });
@@ -954,6 +1004,7 @@ struct umab_engine {
         }
         // edge-degree embedding adjoint
         for (const Chunk& c : chunks) {
+            RepScope rs(this, chunk_rep_rows());
             const EB<S> b = bufs_for<S>(-1, c);
             radial_fwd<S>(ed_rad, c, b, st);
             launch_rotate_back_bwd_t<S>(1, b.rad, gnull<S>(), gnull<S>(), tgt.i(), gp<S>(wig), gp<S>(env),
@@ -1106,6 +1157,9 @@ int32_t umab_set_option(umab_engine* e, const char* name, int64_t value) {
     } else if (n == "fuse_gate") {
         e->opt_fuse_gate = value != 0;
         e->drop_graphs();
+    } else if (n == "jvp_shared_base") {
+        // umab_forces_jvp batches whose images all sit at ONE base geometry (Hessian columns): value-plane GEMMs once
+        e->opt_shared_base = value != 0;
     } else if (n == "cuda_graphs") {
         e->opt_graphs = value != 0;
         if (!e->opt_graphs) e->drop_graphs();
@@ -1135,6 +1189,8 @@ int32_t umab_get_option(umab_engine* e, const char* name, int64_t* value) {
     const std::string n(name);
     if (n == "nosync") *value = e->opt_nosync;
     else if (n == "cuda_graphs") *value = e->opt_graphs;
+    else if (n == "jvp_shared_base") *value = e->opt_shared_base;
+    else if (n == "dedupe_gemms") *value = e->dedupe_gemms;
     else if (n == "fuse_gate") *value = e->opt_fuse_gate;
     else if (n == "graph_replays") *value = e->graph_replays;
     else if (n == "graph_captures") *value = e->graph_captures;

@@ -88,5 +88,8 @@ void launch_head_final_t(GP<S> p2, const float* w4, const float* b4, int n_nodes
                          cudaStream_t st);
 void launch_energy_reduce(const float* node_e, int n_img, int n_atoms, double* energy, cudaStream_t st);
 void launch_tile_int(const int* in, int n, int reps, int* out, cudaStream_t st);
+// Hessian columns of ONE base geometry (all images of a dual-number batch share their value planes):
+void launch_replicate_block(float* base, long long block_floats, int reps, cudaStream_t st);   // block 0 -> blocks 1 .. reps-1
+void launch_same_images(const float* pos, long long n3, int n_img, int* flag, cudaStream_t st); // flag = 1 unless all images equal image 0
 
 }  // namespace umab

@@ -208,8 +208,39 @@ __global__ void tile_int_kernel(const int* __restrict__ in, int n, int reps, int
     if (i < (long long)n * reps) out[i] = in[i % n];
 }
 
+// block 0 of `reps` consecutive blocks of `block4` float4 copied over blocks 1 .. reps-1 (read once, written reps-1 times)
+__global__ void __launch_bounds__(256)
+replicate_block_kernel(float4* __restrict__ base, long long block4, int reps) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < block4; i += stride) {
+        const float4 v = base[i];
+        for (int r = 1; r < reps; ++r) base[r * block4 + i] = v;
+    }
+}
+// flag |= 1 when any image of pos [n_img, n3] differs (bitwise) from image 0
+__global__ void same_images_kernel(const float* __restrict__ pos, long long n3, int n_img, int* __restrict__ flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3 * (n_img - 1)) return;
+    if (__float_as_uint(pos[n3 + i]) != __float_as_uint(pos[i % n3])) atomicOr(flag, 1);
+}
+
 }  // namespace
 
+void launch_replicate_block(float* base, long long block_floats, int reps, cudaStream_t st) {
+    if (reps <= 1 || block_floats <= 0) return;
+    if (block_floats % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) throw CudaError("replicate_block: unaligned block");
+    const long long block4 = block_floats / 4;
+    const long long want = (block4 + 255) / 256;
+    replicate_block_kernel<<<(unsigned)std::min<long long>(want, 148LL * 16), 256, 0, st>>>(reinterpret_cast<float4*>(base), block4, reps);
+    UMAB_LAUNCH_CHECK();
+}
+void launch_same_images(const float* pos, long long n3, int n_img, int* flag, cudaStream_t st) {
+    UMAB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    const long long tot = n3 * (n_img - 1);
+    if (tot <= 0) return;
+    same_images_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pos, n3, n_img, flag);
+    UMAB_LAUNCH_CHECK();
+}
 void launch_tile_int(const int* in, int n, int reps, int* out, cudaStream_t st) {
     long long tot = (long long)n * reps;
     if (tot <= 0) return;

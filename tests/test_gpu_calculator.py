@@ -101,6 +101,37 @@ def test_sharded_analytic_hessian_equals_get_hessian_on_one_rank(built_lib, smal
         assert np.array_equal(a["forces"], b["forces"])
 
 
+@pytest.mark.parametrize("n_atoms,n_cols,kw", [(20, 7, {}), (130, 5, {}), (130, 6, {"workspace_bytes": 9600 * 4 * 9000})])
+def test_jvp_shared_base_gives_identical_bits(built_lib, state4, arch4, n_atoms, n_cols, kw):
+    """Hessian columns of one base geometry ("jvp_shared_base": value-plane GEMMs on one image, block copied to the
+    others): the same bits as the plain dual-number batch -- fp32 split-K path (20 atoms), tensor-core path in one
+    closed chunk and in several chunks (130 atoms) -- and a batch whose images differ is detected on the device and
+    evaluated the plain way."""
+    from pdb2reaction_b200.engine import UmabEngine
+    elem, coords = synth.make_cluster(n_atoms, 21)
+    z, merged = merged_for(state4, arch4, elem)
+    eng = UmabEngine(merged, z, arch4, **kw)
+    pos = torch.from_numpy(coords.astype(np.float32)).cuda().unsqueeze(0).expand(n_cols, n_atoms, 3).contiguous()
+    tan = torch.zeros(n_cols, 3 * n_atoms, device="cuda")
+    tan[torch.arange(n_cols), torch.arange(n_cols) * 5 + 1] = 1.0
+    tan = tan.view(n_cols, n_atoms, 3)
+    f0, df0 = eng.forces_jvp(pos, tan)
+    eng.set_option("jvp_shared_base", 1)
+    c0 = eng.get_option("dedupe_gemms")
+    f1, df1 = eng.forces_jvp(pos, tan)
+    c1 = eng.get_option("dedupe_gemms")
+    assert c1 > c0, "the value-plane GEMMs were not de-duplicated"
+    assert torch.equal(f0, f1) and torch.equal(df0, df1)
+    # images that differ: the device check turns the de-duplication off for the call
+    pos2 = pos.clone()
+    pos2[1, 3, 0] += 1e-3
+    f2, df2 = eng.forces_jvp(pos2, tan)
+    assert eng.get_option("dedupe_gemms") == c1
+    eng.set_option("jvp_shared_base", 0)
+    f3, df3 = eng.forces_jvp(pos2, tan)
+    assert torch.equal(f2, f3) and torch.equal(df2, df3)
+
+
 def test_forces_jvp_matches_central_difference_of_cuda_forces(built_lib, state4, arch4):
     from pdb2reaction_b200.engine import UmabEngine
     elem, imgs = synth.make_string(200, 2, 17)

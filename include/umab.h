@@ -78,7 +78,10 @@ UMAB_API int32_t umab_finalize_weights(umab_engine* e);
  * force below), 1 = brute force, 2 = cell list; both searches return the identical edge list.
  * "nosync" (default 1): sync-free graph build for calls that fit one chunk of the edge workspace;
  * "cuda_graphs" (default 1): capture / replay of launch-bound umab_energy_forces_host calls;
- * "simt_round_fwd" / "simt_round_bwd": operand rounding of the precision study (fp32 SIMT GEMMs only). */
+ * "simt_round_fwd" / "simt_round_bwd": operand rounding of the precision study (fp32 SIMT GEMMs only);
+ * "jvp_shared_base" (default 0): the images of the following umab_forces_jvp calls all sit at ONE geometry (the columns
+ * of an analytic Hessian, reference uma_pysis.py:394-415): verified on the device per call, then the value-plane GEMMs
+ * run on one image and the block is copied to the others -- identical result bits, counter "dedupe_gemms". */
 UMAB_API int32_t umab_set_option(umab_engine* e, const char* name, int64_t value);
 /* Read an option back, or a counter: "graph_replays", "graph_captures", "overflow_retries",
  * "edges_per_image_seen". */

@@ -52,6 +52,35 @@ def test_wigner_is_a_homomorphism_and_rotates_edge_to_y():
     assert np.abs(out - np.array([0, 0, 1.0, 0, 0])).max() < 1e-12
 
 
+def test_real_harmonics_and_wigner_blocks_against_sympy():
+    """External pin of the oracle's spherical-harmonic basis (order, axes, normalisation) and of its Wigner blocks:
+    sympy's real spherical harmonics ``Znm`` (standard physics convention: z polar axis, Condon-Shortley phase).
+    The e3nn basis the oracle restates (m = 0 axis is y, l = 1 ordered (x, y, z)) is the standard one
+    evaluated at the cyclically permuted point (x', y', z') = (z, x, y), WITHOUT the Condon-Shortley phase and in the
+    'component' normalisation: Y_lm^oracle(v) = s_lm sqrt(4 pi / (2l+1)) Znm(l, m, theta', phi'), with the fixed signs
+    s = (-,+,-) for l = 1 and (-,-,+,-,+) for l = 2.  D^l(R) is then checked as the matrix with Y_l(R v) = D^l(R) Y_l(v)
+    on the sympy-evaluated harmonics."""
+    from sympy import N as sN, Znm
+    signs = {1: np.array([-1.0, 1.0, -1.0]), 2: np.array([-1.0, -1.0, 1.0, -1.0, 1.0])}
+
+    def y_sympy(v, l):
+        xp, yp, zp = v[2], v[0], v[1]
+        th, ph = math.acos(zp / np.linalg.norm(v)), math.atan2(yp, xp)
+        z = np.array([float(sN(Znm(l, m, th, ph)).as_real_imag()[0]) for m in range(-l, l + 1)])
+        return signs[l] * math.sqrt(4 * math.pi / (2 * l + 1)) * z
+
+    rng = np.random.default_rng(5)
+    pts = rng.normal(size=(6, 3))
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    rot = Rotation.random(1, random_state=11).as_matrix()[0]
+    for l in (1, 2):
+        ys = np.stack([y_sympy(v, l) for v in pts])
+        assert np.abs(ys - wigner.real_sh(pts, l)).max() < 1e-12
+        d = wigner.d_from_rotation(rot, l)
+        yr = np.stack([y_sympy(rot @ v, l) for v in pts])
+        assert np.abs(yr - ys @ d.T).max() < 1e-12
+
+
 def test_parameter_counts_match_published_uma_s():
     """6.6 M active / ~150 M total, from shapes only (no 150 M allocation)."""
     arch = UMAArch()

@@ -338,8 +338,7 @@ def main():
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}",
-                         hessian_calc_mode="Analytical" if analytic else "FiniteDifference")       # the public API object (e2e path)
+        calc = uma_pysis(model="random:uma-s-1p1", device=f"cuda:{local}")       # the public API object (e2e path)
         calc._ensure_core(elem)
     eng = calc._core.backend.engines[0]
     pos_dev = torch.from_numpy(imgs.astype(np.float32)).cuda()

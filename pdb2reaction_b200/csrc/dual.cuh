@@ -237,13 +237,19 @@ template <> struct AP<float> {
 };
 template <> struct AP<D1> {
     AP<float> v, d;
-    __host__ __device__ AP operator+(long long o) const { return AP{v + o, d + o}; }
+    // Value elements at offsets >= vlim are NOT stored.  Hessian columns of one base geometry (engine: dedupe): the
+    // value-plane GEMM reads the rows of the FIRST image of the chunk only, so the value plane of an A operand is a
+    // dead store for every other image (the tangent plane is always written).  Default: store everything.
+    long long vlim = 0x7fffffffffffffffLL;
+    __host__ __device__ AP operator+(long long o) const {
+        return AP{v + o, d + o, vlim == 0x7fffffffffffffffLL ? vlim : vlim - o};
+    }
     __device__ __forceinline__ void st4(long long i, D4 x) const {
-        v.st4(i, x.v);
+        if (i < vlim) v.st4(i, x.v);
         d.st4(i, x.d);
     }
     template <bool PL> __device__ __forceinline__ void st4t(long long i, D4 x) const {
-        v.template st4t<PL>(i, x.v);
+        if (i < vlim) v.template st4t<PL>(i, x.v);
         d.template st4t<PL>(i, x.d);
     }
     __host__ __device__ bool planes() const { return v.hi != nullptr; }

@@ -96,6 +96,8 @@ template <> GP<D1> gp<D1>(const TBuf& b, long long off) { return GP<D1>{b.v.f() 
 template <class S> GP<S> gnull();
 template <> GP<float> gnull<float>() { return GP<float>{nullptr}; }
 template <> GP<D1> gnull<D1>() { return GP<D1>{nullptr, nullptr}; }
+inline void value_rows(AP<float>&, long long) {}
+inline void value_rows(AP<D1>& a, long long elems) { a.vlim = elems; }
 template <class S> AP<S> anull();
 template <> AP<float> anull<float>() { return AP<float>{nullptr, nullptr, nullptr}; }
 template <> AP<D1> anull<D1>() { return AP<D1>{{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}; }
@@ -714,6 +716,18 @@ struct umab_engine {
         }
         b.h1f = gp<S>(wH1); b.h2f = gp<S>(wH2);
         b.h1 = ap<S>(wH1, 0, cc * 128, sp); b.h2 = ap<S>(wH2, 0, cc * 128, sp); b.gu = ap<S>(wH1, 0, cc * 128, sp);
+        // Hessian columns of one base geometry: only the first image of the chunk feeds the value-plane GEMMs, so the
+        // value planes of the bf16-plane A operands (consumed by nothing but those GEMMs) are not stored for the others
+        static const bool skip_dead = [] { const char* e = getenv("UMAB_SKIP_DEAD_VALUES"); return !(e && atoi(e) == 0); }();   // A/B switch
+        if (skip_dead && sp && chunk_rep_rows() > 0 && c.n_e > e_img && c.n_e % e_img == 0) {
+            const long long r = e_img;
+            value_rows(b.a0, r * 768); value_rows(b.a1, r * 1024); value_rows(b.a2, r * 512);
+            value_rows(b.b0, r * 384); value_rows(b.b1, r * 512); value_rows(b.b2, r * 256);
+            value_rows(b.gy0, r * 640); value_rows(b.gy1, r * 512); value_rows(b.gy2, r * 256);
+            value_rows(b.gz0, r * 384); value_rows(b.gz1, r * 512); value_rows(b.gz2, r * 256);
+            value_rows(b.grad, r * 1536); value_rows(b.ged, r * 384);
+            value_rows(b.h1, r * 128); value_rows(b.h2, r * 128); value_rows(b.gu, r * 128);
+        }
         return b;
     }
 

@@ -176,6 +176,7 @@ template <> struct GP<float> {
     __device__ __forceinline__ void st4(long long i, float4 x) const { *reinterpret_cast<float4*>(p + i) = x; }
     __device__ __forceinline__ float ld(long long i) const { return p[i]; }
     __device__ __forceinline__ void st(long long i, float x) const { p[i] = x; }
+    __device__ __forceinline__ GP vback(long long) const { return *this; }
 };
 template <> struct GP<D1> {
     float* v;
@@ -196,7 +197,36 @@ template <> struct GP<D1> {
     }
     __device__ __forceinline__ D1 ld(long long i) const { return D1{v[i], d[i]}; }
     __device__ __forceinline__ void st(long long i, D1 x) const { v[i] = x.v; d[i] = x.d; }
+    // value plane stepped back by o elements (ImgShare: read the value of the FIRST image of the chunk); read-only use
+    __device__ __forceinline__ GP vback(long long o) const { return GP{v - o, d}; }
 };
+
+// ------------------------------------------------------------------ Hessian columns of one base geometry
+// All images of the launch hold the same VALUE planes (only the tangents differ), and the tensors that come out of the
+// value-plane GEMMs exist for the first image of the chunk only (engine: dedupe, share).  A kernel launched with
+// n_img > 1 then (a) orders its work so that consecutive CTAs take the SAME rows of consecutive images -- they read the
+// same value rows at the same time, once from HBM and otherwise from L2 -- and (b) reads those tensors through
+// GP::vback(img * rows * width).  n_img <= 1: the plain mapping.  `rows` = rows (edges or nodes) per image.
+struct ImgShare { int n_img; int rows; };
+// row of this warp within the launch (false: nothing to do) and the image it belongs to; wpc warps per CTA
+template <class S>
+__device__ __forceinline__ bool share_row(const ImgShare& sh, int wpc, long long n_rows, long long& row, int& img) {
+    const int w = threadIdx.x >> 5;
+    if (std::is_same<S, float>::value || sh.n_img <= 1) {      // the float kernels keep exactly their plain mapping
+        row = (long long)blockIdx.x * wpc + w;
+        img = 0;
+        return row < n_rows;
+    }
+    const int tile = blockIdx.x / sh.n_img;
+    img = blockIdx.x - tile * sh.n_img;
+    const int r = tile * wpc + w;
+    row = (long long)img * sh.rows + r;
+    return r < sh.rows;
+}
+inline unsigned share_grid(const ImgShare& sh, int wpc, long long n_rows) {
+    if (sh.n_img <= 1) return (unsigned)((n_rows + wpc - 1) / wpc);
+    return (unsigned)(((long long)sh.rows + wpc - 1) / wpc) * (unsigned)sh.n_img;
+}
 // ------------------------------------------------------------------ A-operand outputs
 // An activation that is ONLY consumed as the A operand of a GEMM is written either as plain fp32 (exact SIMT
 // GEMMs, small systems) or directly in the operand format of the tensor-core GEMM: two bf16 planes hi / lo with

@@ -19,6 +19,19 @@ namespace umab {
 
 namespace {
 
+// this warp's row and image: the float kernels keep exactly their plain one-warp-per-row mapping (and code)
+#define UMAB_SHARE_ROW(WPC, N, ROW)                                                   \
+    int ROW;                                                                          \
+    int img = 0;                                                                      \
+    if constexpr (std::is_same<S, float>::value) {                                    \
+        ROW = blockIdx.x * (WPC) + threadIdx.x / 32;                                  \
+        if (ROW >= (N)) return;                                                       \
+    } else {                                                                          \
+        long long row_;                                                               \
+        if (!share_row<S>(sh, (WPC), (N), row_, img)) return;                         \
+        ROW = (int)row_;                                                              \
+    }
+
 // every kernel is a template on the scalar type S: float (energy/forces) or D1 (value + tangent)
 template <class S> struct WigReg { S d1[3][3]; S d2[5][5]; };
 
@@ -174,11 +187,11 @@ __device__ __forceinline__ constexpr int from_l(int l) {
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
-                           long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2) {
+                           long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2, ImgShare sh) {
     using V = typename VecOf<S>::type;
-    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    UMAB_SHARE_ROW(8, n_e, el);
     const int lane = threadIdx.x % 32;
-    if (el >= n_e) return;
+    if (img) rad = rad.vback((long long)img * sh.rows * RAD1);
     const long long e = e0 + el;
     const long long rp = (long long)el * RAD1 + lane * 4;
     const long long i0 = (long long)el * 768 + lane * 4, i1 = (long long)el * 1024 + lane * 4,
@@ -338,11 +351,16 @@ template <int HALF, class S, bool PL>
 __global__ void __launch_bounds__(UMAB_HALF_NW * 32, UMAB_HALF_MINB)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
-                              GP<S> g_x, GP<S> g_wig) {
+                              GP<S> g_x, GP<S> g_wig, ImgShare sh, int e_img) {
     using V = typename VecOf<S>::type;
-    const int nl = blockIdx.x * UMAB_HALF_NW + threadIdx.x / 32;
+    UMAB_SHARE_ROW(UMAB_HALF_NW, n_nodes, nl);       // sh.rows = nodes per image; e_img = edges per image
     const int lane = threadIdx.x % 32;
-    if (nl >= n_nodes) return;
+    if (img) {
+        rad = rad.vback((long long)img * e_img * RAD1);
+        gA0 = gA0.vback((long long)img * e_img * 768);
+        gA1 = gA1.vback((long long)img * e_img * 1024);
+        gA2 = gA2.vback((long long)img * e_img * 512);
+    }
     const int i = node0 + nl;
     V acc_i[9], xr[9];
     const long long xi_p = (long long)i * (9 * C) + lane * 4;
@@ -429,11 +447,15 @@ source_reduce_kernel(const float* __restrict__ G, const int* __restrict__ sptr, 
 // ------------------------------------------------------------------ combine + gate (between the convs)
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(4))
-combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2) {
+combine_gate_fwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, ImgShare sh) {
     using V = typename VecOf<S>::type;
-    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    UMAB_SHARE_ROW(8, n_e, el);
     const int lane = threadIdx.x % 32;
-    if (el >= n_e) return;
+    if (img) {
+        Y0 = Y0.vback((long long)img * sh.rows * 640);
+        Y1 = Y1.vback((long long)img * sh.rows * 512);
+        Y2 = Y2.vback((long long)img * sh.rows * 256);
+    }
     const long long y0 = (long long)el * 640 + lane * 4;
     const long long y1 = (long long)el * 512 + lane * 4;
     const long long y2 = (long long)el * 256 + lane * 4;
@@ -480,11 +502,18 @@ gate_b0_kernel(GP<float> Y0, int n_e, AP<float> B0, float* __restrict__ sg) {
 template <class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(3))
 combine_gate_bwd_kernel(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0, AP<S> gY1,
-                        AP<S> gY2) {
+                        AP<S> gY2, ImgShare sh) {
     using V = typename VecOf<S>::type;
-    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    UMAB_SHARE_ROW(8, n_e, el);
     const int lane = threadIdx.x % 32;
-    if (el >= n_e) return;
+    if (img) {
+        Y0 = Y0.vback((long long)img * sh.rows * 640);
+        Y1 = Y1.vback((long long)img * sh.rows * 512);
+        Y2 = Y2.vback((long long)img * sh.rows * 256);
+        gB0 = gB0.vback((long long)img * sh.rows * 384);
+        gB1 = gB1.vback((long long)img * sh.rows * 512);
+        gB2 = gB2.vback((long long)img * sh.rows * 256);
+    }
     const long long y0 = (long long)el * 640 + lane * 4;
     const long long y1 = (long long)el * 512 + lane * 4;
     const long long y2 = (long long)el * 256 + lane * 4;
@@ -560,11 +589,18 @@ __device__ __forceinline__ void load_zl(GP<S> Z0, GP<S> Z1, GP<S> Z2, long long 
 template <int MODE, class S>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ row_ptr, GP<S> wig, GP<S> env,
-                          float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out) {   // base may alias out
+                          float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out,   // base may alias out
+                          ImgShare sh, int e_img) {
     using V = typename VecOf<S>::type;
-    const int nl = blockIdx.x * 8 + threadIdx.x / 32;
+    UMAB_SHARE_ROW(8, n_nodes, nl);                  // sh.rows = nodes per image; e_img = edges per image
     const int lane = threadIdx.x % 32;
-    if (nl >= n_nodes) return;
+    if (img) {
+        Z0 = Z0.vback((long long)img * e_img * 384);
+        if (MODE == 0) {
+            Z1 = Z1.vback((long long)img * e_img * 512);
+            Z2 = Z2.vback((long long)img * e_img * 256);
+        }
+    }
     const int i = node0 + nl;
     V acc[9];
 #pragma unroll
@@ -605,11 +641,18 @@ rotate_back_reduce_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ 
 template <int MODE, class S, bool PL>
 __global__ void __launch_bounds__(256, min_blocks<S>(2))
 rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt, GP<S> wig, GP<S> env, float scale,
-                       long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env, GP<S> g_wig) {
+                       long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env, GP<S> g_wig,
+                       ImgShare sh) {
     using V = typename VecOf<S>::type;
-    const int el = blockIdx.x * 8 + threadIdx.x / 32;
+    UMAB_SHARE_ROW(8, n_e, el);
     const int lane = threadIdx.x % 32;
-    if (el >= n_e) return;
+    if (img) {
+        Z0 = Z0.vback((long long)img * sh.rows * 384);
+        if (MODE == 0) {
+            Z1 = Z1.vback((long long)img * sh.rows * 512);
+            Z2 = Z2.vback((long long)img * sh.rows * 256);
+        }
+    }
     const long long e = e0 + el;
     // the read-modify-write operands first: their DRAM round trips overlap everything below
     const S tau_old = torque_load<S>(g_wig, e, lane);
@@ -654,9 +697,9 @@ rotate_back_bwd_kernel(GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* __restrict__ tgt
 
 template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
-                                  AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st) {
+                                  AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st, ImgShare sh) {
     if (n_e <= 0) return;
-    gather_rotate_scale_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2);
+    gather_rotate_scale_kernel<S><<<share_grid(sh, 8, n_e), 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2, sh);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
@@ -676,22 +719,22 @@ void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<
 template <class S>
 void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* sptr, const int* sedge, GP<S> wig, GP<S> rad,
                                        long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
-                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st) {
+                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st, ImgShare sh, int e_img) {
     if (n_nodes <= 0) return;
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
-    const dim3 grid((n_nodes + UMAB_HALF_NW - 1) / UMAB_HALF_NW);
+    const dim3 grid(share_grid(sh, UMAB_HALF_NW, n_nodes));
     if (g_rad.planes()) {
         gather_rotate_bwd_half_kernel<1, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
-                                                                        gA1, gA2, g_rad, g_x, g_wig);
+                                                                        gA1, gA2, g_rad, g_x, g_wig, sh, e_img);
         UMAB_LAUNCH_CHECK();
         gather_rotate_bwd_half_kernel<0, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
-                                                                        gA2, g_rad, g_x, g_wig);
+                                                                        gA2, g_rad, g_x, g_wig, sh, e_img);
     } else {
         gather_rotate_bwd_half_kernel<1, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
-                                                                         gA1, gA2, g_rad, g_x, g_wig);
+                                                                         gA1, gA2, g_rad, g_x, g_wig, sh, e_img);
         UMAB_LAUNCH_CHECK();
         gather_rotate_bwd_half_kernel<0, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
-                                                                         gA2, g_rad, g_x, g_wig);
+                                                                         gA2, g_rad, g_x, g_wig, sh, e_img);
     }
     UMAB_LAUNCH_CHECK();
 }
@@ -701,9 +744,10 @@ void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
-void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st) {
+void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st,
+                               ImgShare sh) {
     if (n_e <= 0) return;
-    combine_gate_fwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2);
+    combine_gate_fwd_kernel<S><<<share_grid(sh, 8, n_e), 256, 0, st>>>(Y0, Y1, Y2, n_e, B0, B1, B2, sh);
     UMAB_LAUNCH_CHECK();
 }
 void launch_gate_b0(GP<float> Y0, int n_e, AP<float> B0, float* sg, cudaStream_t st) {
@@ -714,32 +758,32 @@ void launch_gate_b0(GP<float> Y0, int n_e, AP<float> B0, float* sg, cudaStream_t
 
 template <class S>
 void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
-                               AP<S> gY1, AP<S> gY2, cudaStream_t st) {
+                               AP<S> gY1, AP<S> gY2, cudaStream_t st, ImgShare sh) {
     if (n_e <= 0) return;
-    combine_gate_bwd_kernel<S><<<(n_e + 7) / 8, 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2);
+    combine_gate_bwd_kernel<S><<<share_grid(sh, 8, n_e), 256, 0, st>>>(Y0, Y1, Y2, n_e, gB0, gB1, gB2, gY0, gY1, gY2, sh);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* row_ptr, GP<S> wig, GP<S> env,
                                  float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, ImgShare sh, int e_img) {
     if (n_nodes <= 0) return;
-    dim3 grid((n_nodes + 7) / 8);
+    dim3 grid(share_grid(sh, 8, n_nodes));
     if (mode == 0)
-        rotate_back_reduce_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<0, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out, sh, e_img);
     else
-        rotate_back_reduce_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out);
+        rotate_back_reduce_kernel<1, S><<<grid, 256, 0, st>>>(Z0, Z1, Z2, row_ptr, wig, env, scale, e0, node0, n_nodes, base, out, sh, e_img);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
 void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* tgt, GP<S> wig, GP<S> env, float scale,
                               long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env,
-                              GP<S> g_wig, cudaStream_t st) {
+                              GP<S> g_wig, cudaStream_t st, ImgShare sh) {
     if (n_e <= 0) return;
-    dim3 grid((n_e + 7) / 8);
+    dim3 grid(share_grid(sh, 8, n_e));
 #define UMAB_RBB(MODE, PL)                                                                                           \
     rotate_back_bwd_kernel<MODE, S, PL><<<grid, 256, 0, st>>>(Z0, Z1, Z2, tgt, wig, env, scale, e0, n_e, g_out, gZ0, gZ1, \
-                                                               gZ2, g_env, g_wig)
+                                                               gZ2, g_env, g_wig, sh)
     const bool pl = gZ0.planes();
     if (mode == 0) {
         if (pl) UMAB_RBB(0, true); else UMAB_RBB(0, false);
@@ -752,19 +796,19 @@ void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int*
 
 #define UMAB_INST(S)                                                                                                  \
     template void launch_gather_rotate_scale_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, AP<S>,  \
-                                                  AP<S>, AP<S>, cudaStream_t);                                        \
+                                                  AP<S>, AP<S>, cudaStream_t, ImgShare);                              \
     template void launch_gather_rotate_bwd_t<S>(GP<S>, const int*, const int*, GP<S>, GP<S>, long long, int, int,      \
                                                 GP<S>, GP<S>, GP<S>, AP<S>, GP<S>, GP<S>, GP<S>, cudaStream_t);       \
     template void launch_gather_rotate_bwd_closed_t<S>(GP<S>, const int*, const int*, const int*, GP<S>, GP<S>,       \
                                                        long long, int, int, GP<S>, GP<S>, GP<S>, AP<S>, GP<S>, GP<S>,  \
-                                                       cudaStream_t);                                                  \
-    template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, AP<S>, AP<S>, AP<S>, cudaStream_t);           \
+                                                       cudaStream_t, ImgShare, int);                                   \
+    template void launch_combine_gate_fwd_t<S>(GP<S>, GP<S>, GP<S>, int, AP<S>, AP<S>, AP<S>, cudaStream_t, ImgShare); \
     template void launch_combine_gate_bwd_t<S>(GP<S>, GP<S>, GP<S>, int, GP<S>, GP<S>, GP<S>, AP<S>, AP<S>, AP<S>,     \
-                                               cudaStream_t);                                                         \
+                                               cudaStream_t, ImgShare);                                               \
     template void launch_rotate_back_reduce_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long, \
-                                                 int, int, GP<S>, GP<S>, cudaStream_t);                               \
+                                                 int, int, GP<S>, GP<S>, cudaStream_t, ImgShare, int);                \
     template void launch_rotate_back_bwd_t<S>(int, GP<S>, GP<S>, GP<S>, const int*, GP<S>, GP<S>, float, long long,    \
-                                              int, GP<S>, AP<S>, AP<S>, AP<S>, GP<S>, GP<S>, cudaStream_t);
+                                              int, GP<S>, AP<S>, AP<S>, AP<S>, GP<S>, GP<S>, cudaStream_t, ImgShare);
 UMAB_INST(float)
 UMAB_INST(D1)
 #undef UMAB_INST

@@ -246,12 +246,17 @@ struct umab_engine {
     long long e_img = 0;                               // edges per image (dedupe)
     long long dedupe_gemms = 0;                        // value-plane GEMMs run on one image (umab_get_option "dedupe_gemms")
     DevBuf same_flag;
-    // value-plane GEMM on one image + replication, or the plain GEMM
-    void gemm_plane(GemmArgs& g, int k, long long M, long long block_ld, cudaStream_t st) {
+    // Second step (UMAB_SHARE_VALUES, default on): the edge kernels that consume those GEMM outputs read the value rows of
+    // the FIRST image of the chunk (ImgShare, dual.cuh) in an order that lets the images of a batch share them in L2, so
+    // the block is not even copied: per edge the value planes cross HBM once per batch instead of once per column.
+    bool opt_share = [] { const char* e = getenv("UMAB_SHARE_VALUES"); return !(e && atoi(e) == 0); }();
+    bool cur_share = false;                            // inside a chunk whose edge kernels run with ImgShare
+    // value-plane GEMM on one image (+ replication unless its consumers share the block), or the plain GEMM
+    void gemm_plane(GemmArgs& g, int k, long long M, long long block_ld, cudaStream_t st, bool consumers_share = false) {
         if (k == 0 && rep_rows > 0 && M > rep_rows && M % rep_rows == 0 && !g.gate) {
             g.M = (int)rep_rows;
             gemm(g, st);
-            launch_replicate_block(g.Cmat, rep_rows * block_ld, (int)(M / rep_rows), st);
+            if (!(consumers_share && cur_share)) launch_replicate_block(g.Cmat, rep_rows * block_ld, (int)(M / rep_rows), st);
             ++dedupe_gemms;
         } else {
             g.M = (int)M;
@@ -259,11 +264,21 @@ struct umab_engine {
         }
     }
     struct RepScope {                                  // rows per image inside a chunk loop, restored on exit
-        umab_engine* e; long long saved;
-        RepScope(umab_engine* e_, long long rows) : e(e_), saved(e_->rep_rows) { e->rep_rows = rows; }
-        ~RepScope() { e->rep_rows = saved; }
+        umab_engine* e; long long saved; bool saved_share;
+        RepScope(umab_engine* e_, long long rows, bool share) : e(e_), saved(e_->rep_rows), saved_share(e_->cur_share) {
+            e->rep_rows = rows; e->cur_share = share;
+        }
+        ~RepScope() { e->rep_rows = saved; e->cur_share = saved_share; }
     };
     long long chunk_rep_rows() const { return dedupe && chunks_closed ? e_img : 0; }
+    // images of a chunk whose edge kernels share the value planes (0: the plain launch)
+    int chunk_images(const Chunk& c) const {
+        if (!dedupe || !opt_share || !chunks_closed || n_atoms <= 0 || c.n_nodes % n_atoms) return 0;
+        const int k = c.n_nodes / n_atoms;
+        return (k > 1 && (long long)c.n_e == (long long)k * e_img) ? k : 0;
+    }
+    ImgShare share_e(const Chunk& c) const { return ImgShare{chunk_images(c), (int)e_img}; }    // one warp per edge
+    ImgShare share_n(const Chunk& c) const { return ImgShare{chunk_images(c), n_atoms}; }       // one warp per node
     std::vector<Chunk> chunks;
     bool chunks_closed = false;                        // chunks hold whole images (see plan_chunks)
     static bool store_radial_enabled() {               // UMAB_STORE_RADIAL=0: recompute the radial MLP in the backward (A/B)
@@ -442,7 +457,7 @@ struct umab_engine {
             g.A = a.p; g.A_hi = a.hi; g.A_lo = a.lo; g.lda = K; g.W = Wt; g.ldw = K; g.Cmat = plane(Cm, k); g.ldc = ldc;
             g.bias = k == 0 ? bias : nullptr;
             g.N = N; g.K = K; g.accumulate = 0;
-            gemm_plane(g, k, M, ldc, st);
+            gemm_plane(g, k, M, ldc, st, /* every consumer of an mm_ap output is an ImgShare kernel */ true);
         }
     }
     // conv-1 m != 0 GEMM with the gate applied in the epilogue (float, CTA-pair kernel): C = A W^T (fp32, kept) and
@@ -739,7 +754,8 @@ struct umab_engine {
             launch_ln_silu_fwd_t<S>(b.u1, b.h1, r.ln1w, r.ln1b, r.b1, r.t_src, r.t_tgt, zt.i(), src.i() + e0, tgt.i() + e0, c.n_e, st); });
         mm_ap<S>(b.h1, r.w2, 128, 128, b.u2, 128, c.n_e, r.b2, st);
         timed(P_LN_SILU, 2 * lnb, st, [&] {
-            launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st); });
+            launch_ln_silu_fwd_t<S>(b.u2, b.h2, r.ln2w, r.ln2b, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c.n_e, st,
+                                    share_e(c)); });
         mm_ap<S>(b.h2, r.w3, r.n_out, 128, b.rad, r.n_out, c.n_e, r.b3, st);
     }
     // g_rad: [n_e, n_out] A operand; accumulates into g_gauss.  u1 / u2 are the forward pre-activations.
@@ -747,11 +763,12 @@ struct umab_engine {
         mm_ap<S>(g_rad, r.w3_t, 128, r.n_out, b.h2f, 128, c.n_e, nullptr, st);                  // dL/dh_2
         const double lnb = planes<S>() * c.n_e * 128.0 * 4.0;
         timed(P_LN_SILU, 3 * lnb, st, [&] {
-            launch_ln_silu_bwd_t<S>(b.u2, b.h2f, b.gu, r.ln2w, r.ln2b, c.n_e, st); });           // dL/du_2
+            launch_ln_silu_bwd_t<S>(b.u2, b.h2f, b.gu, r.ln2w, r.ln2b, c.n_e, st, share_e(c), true); });           // dL/du_2
         mm_ap<S>(b.gu, r.w2_t, 128, 128, b.h2f, 128, c.n_e, nullptr, st);                        // dL/dh_1
         // dL/du_1 stays fp32: the last GEMM (N = 64, accumulating) runs on the in-kernel-split path
         timed(P_LN_SILU, 3 * lnb, st, [&] {
-            launch_ln_silu_bwd_t<S>(b.u1, b.h2f, ap<S>(wH1, 0, 0, false), r.ln1w, r.ln1b, c.n_e, st); });
+            launch_ln_silu_bwd_t<S>(b.u1, b.h2f, ap<S>(wH1, 0, 0, false), r.ln1w, r.ln1b, c.n_e, st, share_e(c),
+                                    /* u_1 (per-element tables added in place) is per image */ false); });
         mm<S>(b.h1f, 128, r.w1g_t, NB, 128, gp<S>(g_gauss, c.e0 * NB), NB, c.n_e, nullptr, 1, st);
     }
     // conv-1 radial, gather/rotate, conv-1, gate, conv-2 for one chunk (everything up to Z)
@@ -761,7 +778,8 @@ struct umab_engine {
         const double P = planes<S>();
         radial_fwd<S>(w.rad, c, b, st);
         timed(P_GATHER, P * (c.n_e * 15512.0 + c.n_nodes * 4608.0), st, [&] {
-            launch_gather_rotate_scale_t<S>(n1, src.i(), tgt.i(), gp<S>(wig), b.rad, c.e0, c.n_e, b.a0, b.a1, b.a2, st); });
+            launch_gather_rotate_scale_t<S>(n1, src.i(), tgt.i(), gp<S>(wig), b.rad, c.e0, c.n_e, b.a0, b.a1, b.a2, st,
+                                            share_e(c)); });
         mm_ap<S>(b.a0, w.c1m0, 640, 768, b.y0, 640, c.n_e, w.c1m0_b, st);
         if constexpr (std::is_same<S, float>::value) {
             if (opt_fuse_gate && use_tc() && gemm_tc2_gate_epilogue_available() && c.n_e > 0) {
@@ -779,7 +797,7 @@ struct umab_engine {
         mm_ap<S>(b.a1, w.c1m1, 512, 1024, b.y1, 512, c.n_e, nullptr, st);
         mm_ap<S>(b.a2, w.c1m2, 256, 512, b.y2, 256, c.n_e, nullptr, st);
         timed(P_COMBINE, P * c.n_e * (YW + 1152) * 4.0, st, [&] {
-            launch_combine_gate_fwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, st); });
+            launch_combine_gate_fwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.b0, b.b1, b.b2, st, share_e(c)); });
     conv2:
         mm_ap<S>(b.b0, w.c2m0, 384, 384, b.z0, 384, c.n_e, w.c2m0_b, st);
         mm_ap<S>(b.b1, w.c2m1, 512, 512, b.z1, 512, c.n_e, nullptr, st);
@@ -801,7 +819,7 @@ struct umab_engine {
         else if (!store_radial_enabled()) radial_fwd<S>(w.rad, c, b, st);
         timed(P_ROTBACK_BWD, P * (c.n_e * (2 * ZW * 4.0 + 2 * 148.0 + 8.0) + c.n_nodes * 4608.0), st, [&] {
             launch_rotate_back_bwd_t<S>(0, b.z0, b.z1, b.z2, tgt.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0, c.n_e, g_out,
-                                        b.gz0, b.gz1, b.gz2, gp<S>(g_env), gp<S>(g_wig), st); });
+                                        b.gz0, b.gz1, b.gz2, gp<S>(g_env), gp<S>(g_wig), st, share_e(c)); });
         if (cfg.debug && !use_tc()) {
             const std::string p = "bwd.l" + std::to_string(layer) + ".";
             save_dbg_rows(p + "gz0", plane(b.gb0, 0) /* same memory as gz0 in fp32 mode */, c.n_e, 384, c.e0, n_edges, st);
@@ -810,7 +828,7 @@ struct umab_engine {
         mm_ap<S>(b.gz1, w.c2m1_t, 512, 512, b.gb1, 512, c.n_e, nullptr, st);
         mm_ap<S>(b.gz2, w.c2m2_t, 256, 256, b.gb2, 256, c.n_e, nullptr, st);
         timed(P_COMBINE_BWD, P * c.n_e * (YW * 4.0 * 2 + 4608.0), st, [&] {
-            launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.gb0, b.gb1, b.gb2, b.gy0, b.gy1, b.gy2, st); });
+            launch_combine_gate_bwd_t<S>(b.y0, b.y1, b.y2, c.n_e, b.gb0, b.gb1, b.gb2, b.gy0, b.gy1, b.gy2, st, share_e(c)); });
         if (cfg.debug && !use_tc()) {
             const std::string p = "bwd.l" + std::to_string(layer) + ".";
             save_dbg_rows(p + "gb0", plane(b.gb0, 0), c.n_e, 384, c.e0, n_edges, st);
@@ -827,7 +845,8 @@ struct umab_engine {
         if (chunks_closed)
             timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 6 * 144.0 + 8.0) + c.n_nodes * 5 * 4608.0), st, [&] {
                 launch_gather_rotate_bwd_closed_t<S>(n1, row_ptr.i(), sptr.i(), sedge.i(), gp<S>(wig), b.rad, c.e0, c.node0,
-                                                     c.n_nodes, b.ga0, b.ga1, b.ga2, b.grad, g_n1, gp<S>(g_wig), st); });
+                                                     c.n_nodes, b.ga0, b.ga1, b.ga2, b.grad, g_n1, gp<S>(g_wig), st,
+                                                     share_n(c), (int)e_img); });
         else
         timed(P_GATHER_BWD, P * (c.n_e * (9216.0 + 2 * 6144.0 + 4608.0 + 3 * 144.0 + 4.0) + c.n_nodes * 2 * 4608.0), st, [&] {
             launch_gather_rotate_bwd_t<S>(n1, row_ptr.i(), src.i(), gp<S>(wig), b.rad, c.e0, c.node0, c.n_nodes, b.ga0, b.ga1,
@@ -933,12 +952,12 @@ struct umab_engine {
         launch_embed(sphere_emb, csd, zt.i(), n_nodes, xs[0].v.f(), st);
         if (std::is_same<S, D1>::value) UMAB_CUDA(cudaMemsetAsync(xs[0].d.p, 0, nf, st));
         for (const Chunk& c : chunks) {
-            RepScope rs(this, chunk_rep_rows());
+            RepScope rs(this, chunk_rep_rows(), chunk_images(c) > 1);
             const EB<S> b = bufs_for<S>(-1, c);
             radial_fwd<S>(ed_rad, c, b, st);
             launch_rotate_back_reduce_t<S>(1, b.rad, gnull<S>(), gnull<S>(), row_ptr.i(), gp<S>(wig), gp<S>(env),
                                            1.0f / cfg.edge_degree_rescale, c.e0, c.node0, c.n_nodes, gp<S>(xs[0]),
-                                           gp<S>(xs[0]), st);
+                                           gp<S>(xs[0]), st, share_n(c), (int)e_img);
         }
         save_dbg("x0", xs[0].v.p, (size_t)n_nodes * 9 * C, st);
         save_dbg("gauss", gauss.v.p, (size_t)n_edges * NB, st);
@@ -951,12 +970,12 @@ struct umab_engine {
             launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);
             save_dbg("l" + std::to_string(l) + ".n1", nbuf.v.p, (size_t)n_nodes * 9 * C, st);
             for (const Chunk& c : chunks) {
-                RepScope rs(this, chunk_rep_rows());
+                RepScope rs(this, chunk_rep_rows(), chunk_images(c) > 1);
                 edge_fwd_chunk<S>(w, gp<S>(nbuf), c, l, true, st);
                 const EB<S> b = bufs_for<S>(l, c);
                 timed(P_ROTBACK, planes<S>() * (c.n_e * (ZW * 4.0 + 148.0) + c.n_nodes * 9216.0), st, [&] {
                     launch_rotate_back_reduce_t<S>(0, b.z0, b.z1, b.z2, row_ptr.i(), gp<S>(wig), gp<S>(env), 1.0f, c.e0,
-                                                   c.node0, c.n_nodes, gp<S>(xs[l]), gp<S>(x1s[l]), st); });
+                                                   c.node0, c.n_nodes, gp<S>(xs[l]), gp<S>(x1s[l]), st, share_n(c), (int)e_img); });
             }
             save_dbg("l" + std::to_string(l) + ".x1", x1s[l].v.p, (size_t)n_nodes * 9 * C, st);
             launch_rms_fwd_t<S>(gp<S>(x1s[l]), w.n2w, w.n2b, nullptr, n_nodes, gp<S>(nbuf), st);
@@ -1006,7 +1025,7 @@ struct umab_engine {
             // Edgewise adjoint
             launch_rms_fwd_t<S>(gp<S>(xs[l]), w.n1w, w.n1b, csd, n_nodes, gp<S>(nbuf), st);         // recompute n1
             for (const Chunk& c : chunks) {
-                RepScope rs(this, chunk_rep_rows());
+                RepScope rs(this, chunk_rep_rows(), chunk_images(c) > 1);
                 edge_bwd_chunk<S>(w, gp<S>(nbuf), c, l, gp<S>(gx1), gp<S>(gn), st);
             }
             if (!chunks_closed) timed(P_SRC_REDUCE, planes<S>() * (n_edges * 4612.0 + n_nodes * 9216.0), st, [&] {
@@ -1018,12 +1037,12 @@ struct umab_engine {
         }
         // edge-degree embedding adjoint
         for (const Chunk& c : chunks) {
-            RepScope rs(this, chunk_rep_rows());
+            RepScope rs(this, chunk_rep_rows(), chunk_images(c) > 1);
             const EB<S> b = bufs_for<S>(-1, c);
             radial_fwd<S>(ed_rad, c, b, st);
             launch_rotate_back_bwd_t<S>(1, b.rad, gnull<S>(), gnull<S>(), tgt.i(), gp<S>(wig), gp<S>(env),
                                         1.0f / cfg.edge_degree_rescale, c.e0, c.n_e, gp<S>(gx), b.ged, anull<S>(),
-                                        anull<S>(), gp<S>(g_env), gp<S>(g_wig), st);
+                                        anull<S>(), gp<S>(g_env), gp<S>(g_wig), st, share_e(c));
             radial_bwd<S>(ed_rad, c, b, b.ged, st);
         }
         save_dbg("g_gauss", g_gauss.v.p, (size_t)n_edges * NB, st);

@@ -39,14 +39,15 @@ void launch_force_reduce(const float* g_vec, const int* row_ptr, const int* sptr
 template <class S>
 void launch_ln_silu_fwd_t(GP<S> u, AP<S> h, const float* gamma, const float* beta, const float* bias,
                           const float* t_src, const float* t_tgt, const int* z, const int* src, const int* tgt,
-                          int rows, cudaStream_t st);
+                          int rows, cudaStream_t st, ImgShare sh = ImgShare{0, 0});
 template <class S>
-void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st);
+void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st,
+                          ImgShare sh = ImgShare{0, 0}, bool share_u = true);
 
 // ---- edge_ops.cu
 template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
-                                  AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st);
+                                  AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st, ImgShare sh = ImgShare{0, 0});
 template <class S>
 void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<S> wig, GP<S> rad, long long e0,
                                 int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad, GP<S> G,
@@ -54,23 +55,24 @@ void launch_gather_rotate_bwd_t(GP<S> x, const int* row_ptr, const int* src, GP<
 template <class S>
 void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* sptr, const int* sedge, GP<S> wig, GP<S> rad,
                                        long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
-                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st);
+                                       GP<S> g_x, GP<S> g_wig, cudaStream_t st, ImgShare sh = ImgShare{0, 0}, int e_img = 0);
 void launch_source_reduce(const float* G, const int* sptr, const int* sedge, int n_nodes, float* g_x, cudaStream_t st);
 template <class S>
-void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st);
+void launch_combine_gate_fwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, AP<S> B0, AP<S> B1, AP<S> B2, cudaStream_t st,
+                               ImgShare sh = ImgShare{0, 0});
 // fused-gate path: m = 0 part of the combine + sigmoid(gates) [n_e, 256] for the GEMM epilogues
 void launch_gate_b0(GP<float> Y0, int n_e, AP<float> B0, float* sg, cudaStream_t st);
 template <class S>
 void launch_combine_gate_bwd_t(GP<S> Y0, GP<S> Y1, GP<S> Y2, int n_e, GP<S> gB0, GP<S> gB1, GP<S> gB2, AP<S> gY0,
-                               AP<S> gY1, AP<S> gY2, cudaStream_t st);
+                               AP<S> gY1, AP<S> gY2, cudaStream_t st, ImgShare sh = ImgShare{0, 0});
 template <class S>
 void launch_rotate_back_reduce_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* row_ptr, GP<S> wig, GP<S> env,
                                  float scale, long long e0, int node0, int n_nodes, GP<S> base, GP<S> out,
-                                 cudaStream_t st);
+                                 cudaStream_t st, ImgShare sh = ImgShare{0, 0}, int e_img = 0);
 template <class S>
 void launch_rotate_back_bwd_t(int mode, GP<S> Z0, GP<S> Z1, GP<S> Z2, const int* tgt, GP<S> wig, GP<S> env, float scale,
                               long long e0, int n_e, GP<S> g_out, AP<S> gZ0, AP<S> gZ1, AP<S> gZ2, GP<S> g_env,
-                              GP<S> g_wig, cudaStream_t st);
+                              GP<S> g_wig, cudaStream_t st, ImgShare sh = ImgShare{0, 0});
 
 // ---- node_ops.cu
 void launch_embed(const float* sphere_emb, const float* csd, const int* z, int n_nodes, float* x, cudaStream_t st);

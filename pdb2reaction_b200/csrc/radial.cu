@@ -23,10 +23,25 @@ template <class S>
 __global__ void __launch_bounds__(256)
 ln_silu_fwd_kernel(GP<S> u, AP<S> h, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ bias, const float* __restrict__ t_src, const float* __restrict__ t_tgt,
-                   const int* __restrict__ z, const int* __restrict__ src, const int* __restrict__ tgt, int rows) {
+                   const int* __restrict__ z, const int* __restrict__ src, const int* __restrict__ tgt, int rows_all,
+                   ImgShare sh) {
     using V = typename VecOf<S>::type;
-    const int row0 = (blockIdx.x * 8 + threadIdx.x / 32) * RPW;
+    // a warp takes RPW consecutive rows of ONE image (sh: groups of RPW rows per image; u = GEMM output of image 0)
+    long long grp;
+    int img;
+    ImgShare shg = sh;
+    shg.rows = (sh.rows + RPW - 1) / RPW;
+    if (!share_row<S>(shg, 8, ((long long)rows_all + RPW - 1) / RPW, grp, img)) return;
     const int lane = threadIdx.x % 32;
+    int row0, rows;                                     // this warp's first row and the end of its image (or of the launch)
+    if (sh.n_img > 1) {
+        row0 = img * sh.rows + (int)(grp - (long long)img * shg.rows) * RPW;
+        rows = (img + 1) * sh.rows;
+        u = u.vback((long long)img * sh.rows * 128);
+    } else {
+        row0 = (int)grp * RPW;
+        rows = rows_all;
+    }
     if (row0 >= rows) return;
     V v[RPW];
     float4 add[RPW];
@@ -73,10 +88,25 @@ ln_silu_fwd_kernel(GP<S> u, AP<S> h, const float* __restrict__ gamma, const floa
 // g = dL/dh  ->  out = dL/du (the A operand of the next adjoint GEMM; never aliases g)
 template <class S>
 __global__ void __launch_bounds__(256)
-ln_silu_bwd_kernel(GP<S> u, GP<S> g, AP<S> out, const float* __restrict__ gamma, const float* __restrict__ beta, int rows) {
+ln_silu_bwd_kernel(GP<S> u, GP<S> g, AP<S> out, const float* __restrict__ gamma, const float* __restrict__ beta, int rows_all,
+                   ImgShare sh, bool share_u) {
     using V = typename VecOf<S>::type;
-    const int row0 = (blockIdx.x * 8 + threadIdx.x / 32) * RPW;
+    long long grp;
+    int img;
+    ImgShare shg = sh;
+    shg.rows = (sh.rows + RPW - 1) / RPW;
+    if (!share_row<S>(shg, 8, ((long long)rows_all + RPW - 1) / RPW, grp, img)) return;
     const int lane = threadIdx.x % 32;
+    int row0, rows;
+    if (sh.n_img > 1) {
+        row0 = img * sh.rows + (int)(grp - (long long)img * shg.rows) * RPW;
+        rows = (img + 1) * sh.rows;
+        if (share_u) u = u.vback((long long)img * sh.rows * 128);        // u of the table-adding first layer is per image
+        g = g.vback((long long)img * sh.rows * 128);
+    } else {
+        row0 = (int)grp * RPW;
+        rows = rows_all;
+    }
     if (row0 >= rows) return;
     V v[RPW], gg[RPW];
 #pragma unroll
@@ -119,25 +149,33 @@ ln_silu_bwd_kernel(GP<S> u, GP<S> g, AP<S> out, const float* __restrict__ gamma,
 
 }  // namespace
 
+// groups of RPW rows: per image when the launch shares value planes across images (a group never spans two images)
+static inline ImgShare group_share(ImgShare sh) { return ImgShare{sh.n_img, (sh.rows + RPW - 1) / RPW}; }
+
 template <class S>
 void launch_ln_silu_fwd_t(GP<S> u, AP<S> h, const float* gamma, const float* beta, const float* bias,
                           const float* t_src, const float* t_tgt, const int* z, const int* src, const int* tgt,
-                          int rows, cudaStream_t st) {
+                          int rows, cudaStream_t st, ImgShare sh) {
     if (rows <= 0) return;
-    ln_silu_fwd_kernel<S><<<(rows + 8 * RPW - 1) / (8 * RPW), 256, 0, st>>>(u, h, gamma, beta, bias, t_src, t_tgt, z, src, tgt, rows);
+    if (bias || t_src) sh = ImgShare{0, 0};           // this variant updates u in place: every image owns its rows
+    const unsigned grid = share_grid(group_share(sh), 8, ((long long)rows + RPW - 1) / RPW);
+    ln_silu_fwd_kernel<S><<<grid, 256, 0, st>>>(u, h, gamma, beta, bias, t_src, t_tgt, z, src, tgt, rows, sh);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>
-void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st) {
+void launch_ln_silu_bwd_t(GP<S> u, GP<S> g, AP<S> out, const float* gamma, const float* beta, int rows, cudaStream_t st,
+                          ImgShare sh, bool share_u) {
     if (rows <= 0) return;
-    ln_silu_bwd_kernel<S><<<(rows + 8 * RPW - 1) / (8 * RPW), 256, 0, st>>>(u, g, out, gamma, beta, rows);
+    const unsigned grid = share_grid(group_share(sh), 8, ((long long)rows + RPW - 1) / RPW);
+    ln_silu_bwd_kernel<S><<<grid, 256, 0, st>>>(u, g, out, gamma, beta, rows, sh, share_u);
     UMAB_LAUNCH_CHECK();
 }
 template void launch_ln_silu_fwd_t<float>(GP<float>, AP<float>, const float*, const float*, const float*, const float*,
-                                          const float*, const int*, const int*, const int*, int, cudaStream_t);
+                                          const float*, const int*, const int*, const int*, int, cudaStream_t, ImgShare);
 template void launch_ln_silu_fwd_t<D1>(GP<D1>, AP<D1>, const float*, const float*, const float*, const float*,
-                                       const float*, const int*, const int*, const int*, int, cudaStream_t);
-template void launch_ln_silu_bwd_t<float>(GP<float>, GP<float>, AP<float>, const float*, const float*, int, cudaStream_t);
-template void launch_ln_silu_bwd_t<D1>(GP<D1>, GP<D1>, AP<D1>, const float*, const float*, int, cudaStream_t);
+                                       const float*, const int*, const int*, const int*, int, cudaStream_t, ImgShare);
+template void launch_ln_silu_bwd_t<float>(GP<float>, GP<float>, AP<float>, const float*, const float*, int, cudaStream_t,
+                                          ImgShare, bool);
+template void launch_ln_silu_bwd_t<D1>(GP<D1>, GP<D1>, AP<D1>, const float*, const float*, int, cudaStream_t, ImgShare, bool);
 
 }  // namespace umab

@@ -286,7 +286,10 @@ template <> struct AP<D1> {
 };
 
 // occupancy hint: the float instantiations keep the register budgets of the hand-tuned float kernels
-template <class S> constexpr int min_blocks(int for_float) { return std::is_same<S, float>::value ? for_float : 1; }
+#ifndef UMAB_D1_MINB
+#define UMAB_D1_MINB 1
+#endif
+template <class S> constexpr int min_blocks(int for_float) { return std::is_same<S, float>::value ? for_float : UMAB_D1_MINB; }
 
 inline GP<float> gpf(const float* p) { return GP<float>{const_cast<float*>(p)}; }
 

@@ -184,8 +184,10 @@ __device__ __forceinline__ constexpr int from_l(int l) {
 // Processed one l block at a time (l = 0, then the 3x3, then the 5x5 Wigner block) so that only one block of
 // Wigner scalars and node rows is live: the kernel stays inside 80 registers (3 CTAs per SM) with the bf16
 // hi/lo operand stores.
+// (dual-number instantiation: 2 CTAs per SM at 128 registers with 248 B of spills measured 27.9 ms against 32.0 ms for
+// 1 CTA at 194 registers in a shared-base batch of 40 Hessian columns; the same cap made rotate_back_* / combine_gate_bwd slower)
 template <class S>
-__global__ void __launch_bounds__(256, min_blocks<S>(3))
+__global__ void __launch_bounds__(256, std::is_same<S, float>::value ? 3 : 2)
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
                            long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2, ImgShare sh) {
     using V = typename VecOf<S>::type;
@@ -347,8 +349,11 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
 // measured on one box (tools/gpu_ab_libs.sh): 8 warps x 1 CTA (204 / 238 registers, no spills) 60.0 / 60.7 ms per C4 step;
 // 6 x 2 and 4 x 3 (168 registers, 200-280 B of spills, 12 resident warps) 70.1 / 69.9 and 69.6 / 68.4 ms
 #endif
+#ifndef UMAB_HALF_MINB_D1
+#define UMAB_HALF_MINB_D1 1     // the dual-number instantiation (Hessian columns)
+#endif
 template <int HALF, class S, bool PL>
-__global__ void __launch_bounds__(UMAB_HALF_NW * 32, UMAB_HALF_MINB)
+__global__ void __launch_bounds__(UMAB_HALF_NW * 32, std::is_same<S, float>::value ? UMAB_HALF_MINB : UMAB_HALF_MINB_D1)
 gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* __restrict__ elist, GP<S> wig, GP<S> rad,
                               long long e0, int node0, int n_nodes, GP<S> gA0, GP<S> gA1, GP<S> gA2, AP<S> g_rad,
                               GP<S> g_x, GP<S> g_wig, ImgShare sh, int e_img) {

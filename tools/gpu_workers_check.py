@@ -20,3 +20,5 @@ h1 = uma_pysis(model="random:uma-s-1p1", workers=1, freeze_atoms=list(range(290)
 print("hessian", tuple(h.shape), h.dtype, h.device, float(h.abs().max()), "workers=2 equals workers=1:", torch.equal(h, h1.to(h.device)))
 ha = uma_pysis(model="random:uma-s-1p1", workers=2, freeze_atoms=list(range(290)), hessian_calc_mode="Analytical").get_hessian(elem, c[0])["hessian"]
 print("analytic vs FD (workers=2): max abs diff", float((ha - h).abs().max()), "of", float(h.abs().max()))
+ha1 = uma_pysis(model="random:uma-s-1p1", workers=1, freeze_atoms=list(range(290)), hessian_calc_mode="Analytical").get_hessian(elem, c[0])["hessian"]
+print("analytic workers=2 equals workers=1:", torch.equal(ha, ha1.to(ha.device)))

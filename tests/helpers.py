@@ -45,6 +45,11 @@ class SpringBackend:
         h = torch.autograd.functional.hessian(lambda v: self._e(v.view(-1, 3)), x.reshape(-1))
         return h.numpy()
 
+
+class SpringBackendAnalytic(SpringBackend):
+    """SpringBackend plus the analytic-column entry point of CudaBackend (a backend WITHOUT it makes the calculator fall
+    back to finite differences with a warning: test_calculator_contract.py)."""
+
     def hessian_columns(self, coord_ang, dofs):
         """Analytic-mode stand-in of ``CudaBackend.hessian_columns``: rows k of the exact Hessian at the fp32-rounded
         geometry, as float32 [len(dofs), 3N]."""

@@ -96,7 +96,7 @@ def _hess_worker(rank, world, port, frozen, partial, q):
 def _ahess_worker(rank, world, port, frozen, partial, q):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
-    from helpers import SpringBackend
+    from helpers import SpringBackendAnalytic as SpringBackend
     from pdb2reaction_b200 import uma_pysis
     from pdb2reaction_b200.sharding import sharded_analytic_hessian
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

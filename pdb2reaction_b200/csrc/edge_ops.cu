@@ -336,6 +336,113 @@ gather_rotate_bwd_kernel(GP<S> x, const int* __restrict__ row_ptr, const int* __
     for (int r = 0; r < 9; ++r) g_x.st4(xi_p + r * C, acc_i[r]);
 }
 
+// One edge of gather_rotate_bwd_half, one l block at a time: the SAME operations in the SAME order per accumulator as the
+// all-at-once body below (identical bits), but only one Wigner block, its rows of y and of the gradient are live at a
+// time.  Used by the dual-number instantiation, whose all-at-once body needs ~360 registers (1 KB of spills).
+// The node's own rows are re-read per block (L1 hits) and the nine row accumulators live in shared memory
+// (acc_sm: this lane's slots, row r at [(2 r) * 32] (value) and [(2 r + 1) * 32] (tangent)).
+__device__ __forceinline__ void acc_add(float4* acc_sm, int r, D4 g) {
+    acc_sm[(2 * r) * 32] = f4add(acc_sm[(2 * r) * 32], g.v);
+    acc_sm[(2 * r + 1) * 32] = f4add(acc_sm[(2 * r + 1) * 32], g.d);
+}
+template <int HALF, class S, bool PL, class V>
+__device__ __forceinline__ void half_edge_blocked(GP<S> x, long long xi_p, GP<S> wig, long long e, const GP<S>* gbufs, GP<S> rad,
+                                                  long long rp, int lane, AP<S> g_rad, float4* acc_sm, TorqueAcc<V>& tq) {
+    auto ga_of = [&](int kk) { return gbufs[a_buf(kk)].ldg4(a_off(kk) + HALF * C + lane * 4); };
+    auto rv_of = [&](int kk) { return rad.ldg4(rp + r_off(kk) + HALF * C); };
+    asm volatile("" : "+l"(xi_p));       // the rows are re-read per edge on purpose: do not hoist them out of the edge loop
+    {   // l = 0 (m-primary row 0): y = x, the product is added as it is (vmul_unfused)
+        const V ga = ga_of(0), rv = rv_of(0);
+        V g0 = vzero<V>();
+        vfmav(g0, ga, x.ldg4(xi_p));
+        g_rad.template st4t<PL>(rp + HALF * C, g0);
+        acc_add(acc_sm, 0, vmul_unfused(ga, rv));
+    }
+    asm volatile("" ::: "memory");     // phase boundary: keeps the loads of the next block out of this one's live range
+    {   // l = 1: m-primary rows 1, 3, 5 (ascending, as the all-at-once loop visits them)
+        S d[9];
+        load_wig_part<S, 0, 9>(wig, e, d);
+        V y[3], gm[3];
+        {
+            V xr[3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) xr[b] = x.ldg4(xi_p + (1 + b) * C);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+            y[a] = vzero<V>();
+#pragma unroll
+            for (int b = 0; b < 3; ++b) vfma(y[a], d[a * 3 + b], xr[b]);
+            }
+        }
+        V g1 = vzero<V>(), g3 = vzero<V>();
+        {
+            constexpr int ks[3] = {1, 3, 5};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int kk = ks[j], a = to_m(kk) - 1;
+                const V ga = ga_of(kk), rv = rv_of(kk);
+                if (kk == 1) vfmav(g1, ga, y[a]); else vfmav(g3, ga, y[a]);
+                gm[a] = vmul(ga, rv);
+            }
+        }
+        g_rad.template st4t<PL>(rp + 256 + HALF * C, g1);
+        g_rad.template st4t<PL>(rp + 768 + HALF * C, g3);
+        vfmav(tq.x1, gm[2], y[1]); vfnmav(tq.x1, gm[1], y[2]);
+        vfmav(tq.z1, gm[1], y[0]); vfnmav(tq.z1, gm[0], y[1]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            V gx = vzero<V>();
+#pragma unroll
+            for (int b = 0; b < 3; ++b) vfma(gx, d[b * 3 + a], gm[b]);
+            acc_add(acc_sm, 1 + a, gx);
+        }
+    }
+    asm volatile("" ::: "memory");
+    {   // l = 2: m-primary rows 2, 4, 6, 7, 8
+        S d[25];
+        load_wig_part<S, 9, 25>(wig, e, d);
+        V y[5], gm[5];
+        {
+            V xr[5];
+#pragma unroll
+            for (int b = 0; b < 5; ++b) xr[b] = x.ldg4(xi_p + (4 + b) * C);
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                y[a] = vzero<V>();
+#pragma unroll
+                for (int b = 0; b < 5; ++b) vfma(y[a], d[a * 5 + b], xr[b]);
+            }
+        }
+        V g2 = vzero<V>(), g4 = vzero<V>(), g5 = vzero<V>();
+        {
+            constexpr int ks[5] = {2, 4, 6, 7, 8};
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int kk = ks[j], a = to_m(kk) - 4;
+                const V ga = ga_of(kk), rv = rv_of(kk);
+                if (kk == 2) vfmav(g2, ga, y[a]); else if (kk < 7) vfmav(g4, ga, y[a]); else vfmav(g5, ga, y[a]);
+                gm[a] = vmul(ga, rv);
+            }
+        }
+        g_rad.template st4t<PL>(rp + 512 + HALF * C, g2);
+        g_rad.template st4t<PL>(rp + 1024 + HALF * C, g4);
+        g_rad.template st4t<PL>(rp + 1280 + HALF * C, g5);
+        vfmav(tq.x1, gm[0], y[1]); vfnmav(tq.x1, gm[1], y[0]);
+        vfmav(tq.x1, gm[4], y[3]); vfnmav(tq.x1, gm[3], y[4]);
+        vfmav(tq.xs, gm[3], y[2]); vfnmav(tq.xs, gm[2], y[3]);
+        vfmav(tq.z1, gm[3], y[0]); vfnmav(tq.z1, gm[0], y[3]);
+        vfmav(tq.z1, gm[4], y[1]); vfnmav(tq.z1, gm[1], y[4]);
+        vfmav(tq.zs, gm[2], y[1]); vfnmav(tq.zs, gm[1], y[2]);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            V gx = vzero<V>();
+#pragma unroll
+            for (int b = 0; b < 5; ++b) vfma(gx, d[b * 5 + a], gm[b]);
+            acc_add(acc_sm, 4 + a, gx);
+        }
+    }
+}
+
 // ---- split form for CLOSED chunks (every out-edge of a node of the chunk lies inside the chunk: whole images).
 // The source half of the adjoint is then reduced by SOURCE node as well, so the per-edge buffer G [E,9,128] and the
 // source_reduce pass disappear (9.2 KB less HBM traffic per edge and layer, 4.6 KB less memory per edge), and the
@@ -369,8 +476,17 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
     const int i = node0 + nl;
     V acc_i[9], xr[9];
     const long long xi_p = (long long)i * (9 * C) + lane * 4;
+    // dual numbers: row accumulators in shared memory, the node's rows re-read per block (half_edge_blocked)
+    constexpr bool kBlocked = !std::is_same<S, float>::value;
+    extern __shared__ float4 half_acc_sm[];
+    float4* const acc_sm = half_acc_sm + (threadIdx.x / 32) * (9 * 2 * 32) + lane;
+    if (kBlocked) {
 #pragma unroll
-    for (int r = 0; r < 9; ++r) { acc_i[r] = vzero<V>(); xr[r] = x.ldg4(xi_p + r * C); }
+        for (int q = 0; q < 18; ++q) acc_sm[q * 32] = f4zero();
+    } else {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) { acc_i[r] = vzero<V>(); xr[r] = x.ldg4(xi_p + r * C); }
+    }
 
     const int k_end = ptr[i + 1];
     for (int k = ptr[i]; k < k_end; ++k) {
@@ -391,10 +507,15 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
             for (int q = 0; q < 2; ++q) gA2.prefetch(en * 512 + q * 256 + HALF * C + lane * 4);
         }
         const S tau_old = torque_load<S>(g_wig, e, lane);
-        const WigReg<S> w = load_wig<S>(wig, e);
         const long long rp = el * RAD1 + lane * 4;
         const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
         TorqueAcc<V> tq = torque_zero<V>();
+        if constexpr (!std::is_same<S, float>::value) {
+            half_edge_blocked<HALF, S, PL, V>(x, xi_p, wig, e, gbufs, rad, rp, lane, g_rad, acc_sm, tq);
+            torque_commit(tq, cst<S>(1.0f), tau_old, g_wig, e, lane);
+            continue;
+        }
+        const WigReg<S> w = load_wig<S>(wig, e);
         V yl[9], gml[9];
         V g_rad_v[6];
         rot_fwd(w, xr, yl);
@@ -419,6 +540,10 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
 #pragma unroll
         for (int r = 0; r < 9; ++r) acc_i[r] = vadd(acc_i[r], gx[r]);
         torque_commit(tq, cst<S>(1.0f), tau_old, g_wig, e, lane);
+    }
+    if constexpr (kBlocked) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) acc_i[r] = V{acc_sm[(2 * r) * 32], acc_sm[(2 * r + 1) * 32]};
     }
     if (HALF == 1) {
 #pragma unroll
@@ -728,17 +853,25 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
     if (n_nodes <= 0) return;
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
     const dim3 grid(share_grid(sh, UMAB_HALF_NW, n_nodes));
+    // dual numbers: the nine row accumulators of every warp live in shared memory (value + tangent: 9216 B per warp)
+    const size_t smem = std::is_same<S, float>::value ? 0 : (size_t)UMAB_HALF_NW * 9 * 2 * 32 * sizeof(float4);
+    if (smem > 48 * 1024) {
+        UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<1, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<0, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<1, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<0, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if (g_rad.planes()) {
-        gather_rotate_bwd_half_kernel<1, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+        gather_rotate_bwd_half_kernel<1, S, true><<<grid, UMAB_HALF_NW * 32, smem, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
                                                                         gA1, gA2, g_rad, g_x, g_wig, sh, e_img);
         UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, true><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+        gather_rotate_bwd_half_kernel<0, S, true><<<grid, UMAB_HALF_NW * 32, smem, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
                                                                         gA2, g_rad, g_x, g_wig, sh, e_img);
     } else {
-        gather_rotate_bwd_half_kernel<1, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
+        gather_rotate_bwd_half_kernel<1, S, false><<<grid, UMAB_HALF_NW * 32, smem, st>>>(x, row_ptr, nullptr, wig, rad, e0, node0, n_nodes, gA0,
                                                                          gA1, gA2, g_rad, g_x, g_wig, sh, e_img);
         UMAB_LAUNCH_CHECK();
-        gather_rotate_bwd_half_kernel<0, S, false><<<grid, UMAB_HALF_NW * 32, 0, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
+        gather_rotate_bwd_half_kernel<0, S, false><<<grid, UMAB_HALF_NW * 32, smem, st>>>(x, sptr, sedge, wig, rad, e0, node0, n_nodes, gA0, gA1,
                                                                          gA2, g_rad, g_x, g_wig, sh, e_img);
     }
     UMAB_LAUNCH_CHECK();

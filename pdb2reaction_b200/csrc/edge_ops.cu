@@ -345,6 +345,18 @@ __device__ __forceinline__ void acc_add(float4* acc_sm, int r, D4 g) {
     acc_sm[(2 * r) * 32] = f4add(acc_sm[(2 * r) * 32], g.v);
     acc_sm[(2 * r + 1) * 32] = f4add(acc_sm[(2 * r + 1) * 32], g.d);
 }
+__device__ __forceinline__ void acc_add(float4* acc_sm, int r, float4 g) { acc_sm[r * 32] = f4add(acc_sm[r * 32], g); }
+__device__ __forceinline__ void acc_get(const float4* acc_sm, int r, D4& out) { out = D4{acc_sm[(2 * r) * 32], acc_sm[(2 * r + 1) * 32]}; }
+__device__ __forceinline__ void acc_get(const float4* acc_sm, int r, float4& out) { out = acc_sm[r * 32]; }
+#ifndef UMAB_HALF_BLOCKED_FLOAT
+// 1: the float instantiation uses the blocked body too.  Measured (same box, C4 step, gather_rotate_bwd family): plain
+// 59.8 / 59.1 ms; blocked at 172 / 202 registers, 8 warps per SM 63.2 / 62.9 ms; blocked at 128 registers (4-24 B of
+// spills), 16 warps per SM 62.1 / 61.5 ms -- the float kernel is HBM-bound and gains nothing from the occupancy, the
+// shared-memory accumulators cost it 3 ms.  Same bits either way (test_gpu_parity green with the blocked build).
+#define UMAB_HALF_BLOCKED_FLOAT 0
+#endif
+template <class S> constexpr bool half_blocked() { return !std::is_same<S, float>::value || UMAB_HALF_BLOCKED_FLOAT; }
+template <class S> constexpr int half_planes() { return std::is_same<S, float>::value ? 1 : 2; }
 template <int HALF, class S, bool PL, class V>
 __device__ __forceinline__ void half_edge_blocked(GP<S> x, long long xi_p, GP<S> wig, long long e, const GP<S>* gbufs, GP<S> rad,
                                                   long long rp, int lane, AP<S> g_rad, float4* acc_sm, TorqueAcc<V>& tq) {
@@ -477,12 +489,12 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
     V acc_i[9], xr[9];
     const long long xi_p = (long long)i * (9 * C) + lane * 4;
     // dual numbers: row accumulators in shared memory, the node's rows re-read per block (half_edge_blocked)
-    constexpr bool kBlocked = !std::is_same<S, float>::value;
+    constexpr bool kBlocked = half_blocked<S>();
     extern __shared__ float4 half_acc_sm[];
-    float4* const acc_sm = half_acc_sm + (threadIdx.x / 32) * (9 * 2 * 32) + lane;
+    float4* const acc_sm = half_acc_sm + (threadIdx.x / 32) * (9 * half_planes<S>() * 32) + lane;
     if (kBlocked) {
 #pragma unroll
-        for (int q = 0; q < 18; ++q) acc_sm[q * 32] = f4zero();
+        for (int q = 0; q < 9 * half_planes<S>(); ++q) acc_sm[q * 32] = f4zero();
     } else {
 #pragma unroll
         for (int r = 0; r < 9; ++r) { acc_i[r] = vzero<V>(); xr[r] = x.ldg4(xi_p + r * C); }
@@ -510,7 +522,7 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
         const long long rp = el * RAD1 + lane * 4;
         const GP<S> gbufs[3] = {gA0 + el * 768, gA1 + el * 1024, gA2 + el * 512};
         TorqueAcc<V> tq = torque_zero<V>();
-        if constexpr (!std::is_same<S, float>::value) {
+        if constexpr (kBlocked) {
             half_edge_blocked<HALF, S, PL, V>(x, xi_p, wig, e, gbufs, rad, rp, lane, g_rad, acc_sm, tq);
             torque_commit(tq, cst<S>(1.0f), tau_old, g_wig, e, lane);
             continue;
@@ -543,7 +555,7 @@ gather_rotate_bwd_half_kernel(GP<S> x, const int* __restrict__ ptr, const int* _
     }
     if constexpr (kBlocked) {
 #pragma unroll
-        for (int r = 0; r < 9; ++r) acc_i[r] = V{acc_sm[(2 * r) * 32], acc_sm[(2 * r + 1) * 32]};
+        for (int r = 0; r < 9; ++r) acc_get(acc_sm, r, acc_i[r]);
     }
     if (HALF == 1) {
 #pragma unroll
@@ -854,7 +866,7 @@ void launch_gather_rotate_bwd_closed_t(GP<S> x, const int* row_ptr, const int* s
     // (a 128-register build of these kernels -- 2 CTAs per SM, ~500 B of spills -- was measured: 111 ms instead of 74)
     const dim3 grid(share_grid(sh, UMAB_HALF_NW, n_nodes));
     // dual numbers: the nine row accumulators of every warp live in shared memory (value + tangent: 9216 B per warp)
-    const size_t smem = std::is_same<S, float>::value ? 0 : (size_t)UMAB_HALF_NW * 9 * 2 * 32 * sizeof(float4);
+    const size_t smem = half_blocked<S>() ? (size_t)UMAB_HALF_NW * 9 * half_planes<S>() * 32 * sizeof(float4) : 0;
     if (smem > 48 * 1024) {
         UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<1, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         UMAB_CUDA(cudaFuncSetAttribute(gather_rotate_bwd_half_kernel<0, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -56,9 +56,9 @@ def parse():
                    help="measure BASELINE.json's second metric instead: wall time of the full FD Hessian of the C3 "
                         "cluster (--hessian-atoms), column blocks sharded over the N ranks, one all_gather")
     p.add_argument("--hessian-atoms", type=int, default=500)
-    p.add_argument("--hessian-mode", choices=["fd", "analytic"], default="fd",
-                   help="fd: the reference's default mode (1 + 6N force evaluations); analytic: the mode BASELINE configs[2] "
-                        "names (3N dual-number forward + backward passes)")
+    p.add_argument("--hessian-mode", choices=["fd", "analytic"], default="analytic",
+                   help="analytic (default): the mode BASELINE configs[2] names (3N dual-number forward + backward passes); "
+                        "fd: the reference's default calculator mode (1 + 6N force evaluations)")
     return p.parse_args()
 
 

@@ -233,9 +233,11 @@ def emit(obj):
 
 
 def run_hessian(args, world, rank, local):
-    """Hessian wall-time (BASELINE.json metric, configs[2]): full FiniteDifference Hessian (1 + 2*3N force evaluations,
-    reference uma_pysis.py:595-686) of an N-atom cluster through the public calculator; with N ranks the active
-    columns shard over the ranks and ONE all_gather of the column blocks follows (sharding.sharded_fd_hessian).
+    """Hessian wall-time (BASELINE.json metric, configs[2]) of an N-atom cluster through the public calculator:
+    --hessian-mode analytic (default; the mode configs[2] names): 3N dual-number forward + backward passes (reference
+    uma_pysis.py:394-415), sharding.sharded_analytic_hessian; fd: the reference's default FiniteDifference mode,
+    1 + 2*3N force evaluations (uma_pysis.py:595-686), sharding.sharded_fd_hessian.  With N ranks the active columns
+    shard over the ranks and ONE all_gather of the column blocks follows.
     A "step" = one full Hessian, coordinates on the host, result a device tensor + D2H of its norm."""
     import warnings
     import torch.distributed as dist

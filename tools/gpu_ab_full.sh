@@ -1,3 +1,6 @@
+#!/bin/bash
+# the whole -m gpu suite, then an A/B of two builds on ONE box, alternating: pdb2reaction_b200/csrc/libumab_prev.so (a copy
+# of an earlier build, placed there by hand) against the current libumab.so; UMAB_LIB selects the build
 set -u
 mkdir -p gpurun_out
 ( time python -m pytest tests -m gpu -q -x ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log

@@ -184,14 +184,21 @@ __device__ __forceinline__ constexpr int from_l(int l) {
 // Processed one l block at a time (l = 0, then the 3x3, then the 5x5 Wigner block) so that only one block of
 // Wigner scalars and node rows is live: the kernel stays inside 80 registers (3 CTAs per SM) with the bf16
 // hi/lo operand stores.
-// (dual-number instantiation: 2 CTAs per SM at 128 registers with 248 B of spills measured 27.9 ms against 32.0 ms for
-// 1 CTA at 194 registers in a shared-base batch of 40 Hessian columns; the same cap made rotate_back_* / combine_gate_bwd slower)
+// (a 128-register cap made the dual-number rotate_back_* / combine_gate_bwd slower; for this kernel see GRS_D1_* below)
+#ifndef GRS_D1_WARPS
+// dual-number instantiation of gather_rotate_scale: warps per CTA, CTAs per SM.  Measured in a shared-base batch of 40
+// Hessian columns: 8 x 1 (194 registers) 32.0 ms, 8 x 2 (128 registers, 248 B of spills) 27.9-29.4 ms, 4 x 3 (168 registers,
+// 48 B of spills, 12 warps per SM) 25.1 ms
+#define GRS_D1_WARPS 4
+#define GRS_D1_MINB 3
+#endif
+template <class S> constexpr int grs_warps() { return std::is_same<S, float>::value ? 8 : GRS_D1_WARPS; }
 template <class S>
-__global__ void __launch_bounds__(256, std::is_same<S, float>::value ? 3 : 2)
+__global__ void __launch_bounds__(grs_warps<S>() * 32, std::is_same<S, float>::value ? 3 : GRS_D1_MINB)
 gather_rotate_scale_kernel(GP<S> x, const int* __restrict__ src, const int* __restrict__ tgt, GP<S> wig, GP<S> rad,
                            long long e0, int n_e, AP<S> A0, AP<S> A1, AP<S> A2, ImgShare sh) {
     using V = typename VecOf<S>::type;
-    UMAB_SHARE_ROW(8, n_e, el);
+    UMAB_SHARE_ROW(grs_warps<S>(), n_e, el);
     const int lane = threadIdx.x % 32;
     if (img) rad = rad.vback((long long)img * sh.rows * RAD1);
     const long long e = e0 + el;
@@ -345,9 +352,9 @@ __device__ __forceinline__ void acc_add(float4* acc_sm, int r, D4 g) {
     acc_sm[(2 * r) * 32] = f4add(acc_sm[(2 * r) * 32], g.v);
     acc_sm[(2 * r + 1) * 32] = f4add(acc_sm[(2 * r + 1) * 32], g.d);
 }
-__device__ __forceinline__ void acc_add(float4* acc_sm, int r, float4 g) { acc_sm[r * 32] = f4add(acc_sm[r * 32], g); }
+[[maybe_unused]] __device__ __forceinline__ void acc_add(float4* acc_sm, int r, float4 g) { acc_sm[r * 32] = f4add(acc_sm[r * 32], g); }
 __device__ __forceinline__ void acc_get(const float4* acc_sm, int r, D4& out) { out = D4{acc_sm[(2 * r) * 32], acc_sm[(2 * r + 1) * 32]}; }
-__device__ __forceinline__ void acc_get(const float4* acc_sm, int r, float4& out) { out = acc_sm[r * 32]; }
+[[maybe_unused]] __device__ __forceinline__ void acc_get(const float4* acc_sm, int r, float4& out) { out = acc_sm[r * 32]; }
 #ifndef UMAB_HALF_BLOCKED_FLOAT
 // 1: the float instantiation uses the blocked body too.  Measured (same box, C4 step, gather_rotate_bwd family): plain
 // 59.8 / 59.1 ms; blocked at 172 / 202 registers, 8 warps per SM 63.2 / 62.9 ms; blocked at 128 registers (4-24 B of
@@ -841,7 +848,7 @@ template <class S>
 void launch_gather_rotate_scale_t(GP<S> x, const int* src, const int* tgt, GP<S> wig, GP<S> rad, long long e0, int n_e,
                                   AP<S> A0, AP<S> A1, AP<S> A2, cudaStream_t st, ImgShare sh) {
     if (n_e <= 0) return;
-    gather_rotate_scale_kernel<S><<<share_grid(sh, 8, n_e), 256, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2, sh);
+    gather_rotate_scale_kernel<S><<<share_grid(sh, grs_warps<S>(), n_e), grs_warps<S>() * 32, 0, st>>>(x, src, tgt, wig, rad, e0, n_e, A0, A1, A2, sh);
     UMAB_LAUNCH_CHECK();
 }
 template <class S>

@@ -101,15 +101,25 @@ def test_sharded_analytic_hessian_equals_get_hessian_on_one_rank(built_lib, smal
         assert np.array_equal(a["forces"], b["forces"])
 
 
-@pytest.mark.parametrize("n_atoms,n_cols,kw", [(20, 7, {}), (130, 5, {}), (130, 6, {"workspace_bytes": 9600 * 4 * 9000})])
+@pytest.mark.parametrize("n_atoms,n_cols,kw", [(20, 7, {}), (130, 5, {}), (130, 6, {"workspace_bytes": 9600 * 4 * 9000}),
+                                               (130, 5, {"images_per_chunk": 2.5}),
+                                               (130, 7, {"images_per_chunk": 3.5, "store_bytes": -1})])
 def test_jvp_shared_base_gives_identical_bits(built_lib, state4, arch4, n_atoms, n_cols, kw):
-    """Hessian columns of one base geometry ("jvp_shared_base": value-plane GEMMs on one image, block copied to the
-    others): the same bits as the plain dual-number batch -- fp32 split-K path (20 atoms), tensor-core path in one
-    closed chunk and in several chunks (130 atoms) -- and a batch whose images differ is detected on the device and
-    evaluated the plain way."""
+    """Hessian columns of one base geometry ("jvp_shared_base": value planes computed and read once per batch): the same
+    bits as the plain dual-number batch -- fp32 split-K path (20 atoms), tensor-core path in one closed chunk, in chunks
+    of one image, in chunks of TWO images (2 + 2 + 1: the value pointers step back relative to the chunk) and in the
+    recompute mode with chunks of two images (130 atoms) -- and a batch whose images differ is detected on the device
+    and evaluated the plain way."""
     from pdb2reaction_b200.engine import UmabEngine
     elem, coords = synth.make_cluster(n_atoms, 21)
     z, merged = merged_for(state4, arch4, elem)
+    kw = dict(kw)
+    if "images_per_chunk" in kw:
+        probe = UmabEngine(merged, z, arch4)
+        e_img = probe.graph(torch.from_numpy(coords.astype(np.float32)).cuda().unsqueeze(0))[0].shape[0]
+        per_edge = (8192 + (2560 if kw.get("store_bytes", 0) < 0 else 0)) * 4 * 2      # engine.cu EDGE_WS_FLOATS (+ recompute), two planes
+        kw["workspace_bytes"] = int(kw.pop("images_per_chunk") * e_img) * per_edge
+        del probe
     eng = UmabEngine(merged, z, arch4, **kw)
     pos = torch.from_numpy(coords.astype(np.float32)).cuda().unsqueeze(0).expand(n_cols, n_atoms, 3).contiguous()
     tan = torch.zeros(n_cols, 3 * n_atoms, device="cuda")
